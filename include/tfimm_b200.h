@@ -1,0 +1,114 @@
+/* tfimm_b200 -- C ABI of the B200 (sm_100a) kernel library behind the tfimm forward path.
+ *
+ * The reference (martinsbruveris/tensorflow-image-models) has no FFI of its own: its device
+ * boundary is inside TensorFlow.  This header is the boundary a maintainer would bind instead
+ * (ctypes stub in INTEGRATION.md; the in-tree binding is
+ * tensorflow-image-models_b200/tfimm/backend/lib.py).  Every entry point names the reference
+ * call site(s) it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every pointer is a DEVICE pointer owned by the caller
+ *   - activations are channels-last: (rows, C) / (B, H, W, C); Dense/conv weights are passed
+ *     pre-transposed as W[N][K] (K contiguous), i.e. the TF kernel (in,out) / (kh,kw,in,out)
+ *     flattened over its leading axes and transposed once at load time
+ *   - dtype codes: TFIMM_F32 / TFIMM_BF16 / TFIMM_U8; bias / gamma / beta / BN vectors are fp32
+ *   - every launch takes the cudaStream_t to enqueue on (as void*); calls are asynchronous
+ *   - return value: 0 = OK, otherwise a TFIMM_ERR_* code; tfimm_b200_last_error() returns a
+ *     thread-local human-readable message.  Nothing here allocates device memory.
+ *   - there is NO CPU fallback: without a B200 these calls fail with a CUDA error.
+ */
+#ifndef TFIMM_B200_H_
+#define TFIMM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFIMM_F32 0
+#define TFIMM_BF16 1
+#define TFIMM_U8 2
+
+#define TFIMM_ACT_NONE 0
+#define TFIMM_ACT_GELU 1    /* exact erf form == Keras "gelu" (tfimm/layers/factory.py:8-9) */
+#define TFIMM_ACT_SWISH 2   /* x * sigmoid(x) */
+#define TFIMM_ACT_RELU 3
+#define TFIMM_ACT_RELU6 4   /* tf.keras.layers.ReLU(max_value=6) (tfimm/layers/factory.py:10-11) */
+#define TFIMM_ACT_TANH 5
+#define TFIMM_ACT_SIGMOID 6
+
+#define TFIMM_OK 0
+#define TFIMM_ERR_INVALID_ARGUMENT 1
+#define TFIMM_ERR_CUDA 2
+#define TFIMM_ERR_UNSUPPORTED 3
+
+/* Library identification / diagnostics. */
+const char* tfimm_b200_version(void);
+const char* tfimm_b200_last_error(void);
+/* Number of SMs of the current device (0 if no device); used by the host to size workspaces. */
+int tfimm_b200_sm_count(void);
+
+/* Dense / 1x1 conv with fused epilogue:  C = residual + gamma * act(A @ W^T + bias).
+ * A:[M,K] bf16 (ld = lda), W:[N,K] bf16 (ld = ldw), C/residual:[M,N] of out_dtype (bf16|f32);
+ * residual may alias C (in-place residual stream).  tcgen05 tensor cores, TMA, fp32 accumulate.
+ * Replaces tf.keras.layers.Dense at tfimm/architectures/vit.py:142-146, swin.py:124-128,343-345,
+ * tfimm/layers/transformers.py:192-205, the classifier heads (vit.py:364-368, swin.py:457-461,
+ * convnext.py:356-360, efficientnet.py:259-263) and 1x1 Conv2D (efficientnet_blocks.py:412-434,
+ * resnet.py:220-248); gamma/residual fuse ConvNeXtBlock's layer-scale + shortcut (convnext.py:226-227).
+ * force_block_n: 0 = auto, else 64/128/256 (testing). */
+int tfimm_b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias,
+                         const float* gamma, const void* residual, int ldr, void* C, int ldc, int M, int N,
+                         int K, int act, int out_dtype, int force_block_n, void* stream);
+
+/* Same contract in fp32 on CUDA cores (precision="fp32" parity mode). */
+int tfimm_b200_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
+                        const float* gamma, const float* residual, int ldr, float* C, int ldc, int M, int N,
+                        int K, int act, void* stream);
+
+/* LayerNorm over the last axis, fp32 statistics (tfimm/layers/factory.py:37-45).
+ * in_stride/out_stride in elements (lets the caller normalise only token 0 of each image:
+ * tfimm/architectures/vit.py:452,462). */
+int tfimm_b200_layernorm(const void* x, int in_dtype, long in_stride, const float* gamma, const float* beta,
+                         void* out, int out_dtype, long out_stride, long rows, int C, float eps, void* stream);
+
+/* LayerNorm per pixel of an NHWC map, written directly in the im2col layout of the following
+ * 2x2 / stride-2 conv: out[(b, y/2, x/2), ((y%2)*2 + x%2)*C + c].
+ * ConvNeXt downsample, tfimm/architectures/convnext.py:257-266,286-295. */
+int tfimm_b200_layernorm_patch2x2(const void* x, int in_dtype, const float* gamma, const float* beta, void* out,
+                                  int out_dtype, int B, int H, int W, int C, float eps, void* stream);
+
+/* Swin PatchMerging gather (neighbour order (0,0),(1,0),(0,1),(1,1)) + LayerNorm over 4C;
+ * tfimm/architectures/swin.py:348-362.  out: (B*H/2*W/2, 4C). */
+int tfimm_b200_patch_merge_ln(const void* x, int in_dtype, const float* gamma, const float* beta, void* out,
+                              int out_dtype, int B, int H, int W, int C, float eps, void* stream);
+
+/* Fused softmax(scale * q k^T) v over the packed qkv projection (B*N, 3*H*dh), column order
+ * [q|k|v] each head-major; out (B*N, H*dh).  tfimm/architectures/vit.py:149-165. bf16, dh == 64. */
+int tfimm_b200_attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
+
+/* fp32 attention with optional additive bias[H,N,N] and mask[nmask,N,N] (window b uses mask b % nmask)
+ * and optional probability output probs[B,H,N,N] (features["attn"], vit.py:163).
+ * Covers vit.py:149-165 and swin.py:172-194 in precision="fp32". */
+int tfimm_b200_attention_f32(const float* qkv, float* out, const float* bias, const float* mask, int nmask,
+                             long B, int N, int H, int dh, float scale, float* probs, void* stream);
+
+/* Non-overlapping p x p patch gather (im2col of Conv2D(k=p, s=p, VALID)); out (B*H/p*W/p, Kpad),
+ * column order (ky, kx, c), zero-padded to Kpad.  Optional fused create_preprocessing:
+ * v = (x*scale - mean[c]) * inv_std[c] (tfimm/models/factory.py:153-169).
+ * tfimm/layers/transformers.py:128-139, convnext.py:319-326. */
+int tfimm_b200_patchify(const void* img, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C,
+                        int p, int Kpad, float scale, const float* mean, const float* inv_std, void* stream);
+
+/* x[b] = concat(cls, [dist], patches[b]) + pos_embed;  tfimm/architectures/vit.py:427-434. */
+int tfimm_b200_assemble_tokens(const void* patches, int patch_dtype, const float* cls, const float* dist,
+                               const float* pos, void* out, int out_dtype, int B, int P, int ntok, int D,
+                               void* stream);
+
+/* Elementwise dtype conversion. */
+int tfimm_b200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFIMM_B200_H_ */

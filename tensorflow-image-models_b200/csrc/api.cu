@@ -1,0 +1,126 @@
+// extern "C" surface of libtfimm_b200.so (declared in include/tfimm_b200.h) plus the
+// error-reporting plumbing shared by every translation unit.
+#include "../../include/tfimm_b200.h"
+
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace tfimm {
+
+namespace {
+thread_local char g_last_error[1024] = "";
+}
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_last_error("CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return kCudaError;
+}
+
+int sm_count() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return 0;
+    }
+    cached = n;
+  }
+  return cached;
+}
+
+// implemented in the other translation units
+int gemm_bf16_dispatch(const void*, int, const void*, int, const float*, const float*, const void*, int, void*,
+                       int, int, int, int, int, int, int, cudaStream_t);
+int gemm_f32(const float*, int, const float*, int, const float*, const float*, const float*, int, float*, int,
+             int, int, int, int, cudaStream_t);
+int layernorm_rows(const void*, int, long, const float*, const float*, void*, int, long, long, int, float,
+                   cudaStream_t);
+int layernorm_patch2x2(const void*, int, const float*, const float*, void*, int, int, int, int, int, float,
+                       cudaStream_t);
+int patch_merge_ln(const void*, int, const float*, const float*, void*, int, int, int, int, int, float,
+                   cudaStream_t);
+int attention_bf16(const void*, void*, int, int, int, int, float, cudaStream_t);
+int attention_f32(const float*, float*, const float*, const float*, int, long, int, int, int, float, float*,
+                  cudaStream_t);
+int patchify(const void*, int, void*, int, int, int, int, int, int, int, float, const float*, const float*,
+             cudaStream_t);
+int assemble_tokens(const void*, int, const float*, const float*, const float*, void*, int, int, int, int, int,
+                    cudaStream_t);
+int cast_tensor(const void*, int, void*, int, long, cudaStream_t);
+
+}  // namespace tfimm
+
+using tfimm::set_last_error;
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* tfimm_b200_version(void) { return "tfimm_b200 0.1.0 (sm_100a)"; }
+const char* tfimm_b200_last_error(void) { return tfimm::g_last_error; }
+int tfimm_b200_sm_count(void) { return tfimm::sm_count(); }
+
+int tfimm_b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
+                         const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act,
+                         int out_dtype, int force_block_n, void* stream) {
+  return tfimm::gemm_bf16_dispatch(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act, out_dtype,
+                                   force_block_n, S(stream));
+}
+
+int tfimm_b200_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias, const float* gamma,
+                        const float* residual, int ldr, float* C, int ldc, int M, int N, int K, int act,
+                        void* stream) {
+  return tfimm::gemm_f32(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act, S(stream));
+}
+
+int tfimm_b200_layernorm(const void* x, int in_dtype, long in_stride, const float* gamma, const float* beta,
+                         void* out, int out_dtype, long out_stride, long rows, int C, float eps, void* stream) {
+  return tfimm::layernorm_rows(x, in_dtype, in_stride, gamma, beta, out, out_dtype, out_stride, rows, C, eps,
+                               S(stream));
+}
+
+int tfimm_b200_layernorm_patch2x2(const void* x, int in_dtype, const float* gamma, const float* beta, void* out,
+                                  int out_dtype, int B, int H, int W, int C, float eps, void* stream) {
+  return tfimm::layernorm_patch2x2(x, in_dtype, gamma, beta, out, out_dtype, B, H, W, C, eps, S(stream));
+}
+
+int tfimm_b200_patch_merge_ln(const void* x, int in_dtype, const float* gamma, const float* beta, void* out,
+                              int out_dtype, int B, int H, int W, int C, float eps, void* stream) {
+  return tfimm::patch_merge_ln(x, in_dtype, gamma, beta, out, out_dtype, B, H, W, C, eps, S(stream));
+}
+
+int tfimm_b200_attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, float scale,
+                              void* stream) {
+  return tfimm::attention_bf16(qkv, out, B, N, H, dh, scale, S(stream));
+}
+
+int tfimm_b200_attention_f32(const float* qkv, float* out, const float* bias, const float* mask, int nmask,
+                             long B, int N, int H, int dh, float scale, float* probs, void* stream) {
+  return tfimm::attention_f32(qkv, out, bias, mask, nmask, B, N, H, dh, scale, probs, S(stream));
+}
+
+int tfimm_b200_patchify(const void* img, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C,
+                        int p, int Kpad, float scale, const float* mean, const float* inv_std, void* stream) {
+  return tfimm::patchify(img, in_dtype, out, out_dtype, B, H, W, C, p, Kpad, scale, mean, inv_std, S(stream));
+}
+
+int tfimm_b200_assemble_tokens(const void* patches, int patch_dtype, const float* cls, const float* dist,
+                               const float* pos, void* out, int out_dtype, int B, int P, int ntok, int D,
+                               void* stream) {
+  return tfimm::assemble_tokens(patches, patch_dtype, cls, dist, pos, out, out_dtype, B, P, ntok, D, S(stream));
+}
+
+int tfimm_b200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream) {
+  return tfimm::cast_tensor(in, in_dtype, out, out_dtype, n, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,427 @@
+// Dense contraction for the tfimm forward path on sm_100a:
+//
+//     C[M,N] = residual[M,N] + gamma[N] * act(A[M,K] @ W[N,K]^T + bias[N])
+//
+// This single kernel replaces every tf.keras.layers.Dense and 1x1 Conv2D the
+// reference calls on the hot path (qkv/proj: tfimm/architectures/vit.py:142-146,
+// swin.py:124-128; fc1/fc2: tfimm/layers/transformers.py:192-205; heads:
+// vit.py:364-368, convnext.py:356-360; 1x1 convs: efficientnet_blocks.py:412-434,
+// resnet.py:220-248) plus the patchify convolutions once their input has been
+// gathered (layers/transformers.py:131-139, convnext.py:259-266,319-326).
+//
+// Design (one persistent CTA per SM, warp-specialised):
+//   warp 0      TMA producer: A/W tiles -> 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1      MMA issuer: tcgen05.mma 128 x BLOCK_N x 16, fp32 accumulators in TMEM,
+//               two accumulator stages so the epilogue of tile i overlaps the MMAs of i+1
+//   warps 2..5  epilogue: tcgen05.ld -> bias/act/gamma/residual in registers ->
+//               swizzled smem slab -> TMA store (one 32-row slab per warp, so no
+//               cross-warp barrier).  The residual tile is TMA-loaded into the same
+//               slab and may alias the output (in-place residual stream).
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace tfimm {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle span
+constexpr int kUmmaK = 16;
+constexpr int kNumEpiWarps = 4;
+constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
+constexpr int kSlabBytes = 32 * 128;  // 32 rows x 128 B
+constexpr int kSlabBufs = 2;
+constexpr int kAccStages = 2;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kSlabTotal = kNumEpiWarps * kSlabBufs * kSlabBytes;
+  static constexpr int kNumBarriers = 2 * kStages + 2 * kAccStages + kNumEpiWarps * kSlabBufs;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kSlabTotal + kNumBarriers * 8 + 16 + 1024 /*alignment slack*/;
+  static constexpr uint32_t kTmemCols = kAccStages * BLOCK_N;  // 512 / 256 / 128
+};
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;   // [N] or null
+  const float* gamma;  // [N] or null
+  int act;
+  int has_res;
+};
+
+template <int BLOCK_N, typename OutT>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c,
+                         const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int CH = 128 / (int)sizeof(OutT);  // output columns per 128-byte slab row
+  constexpr int NCH = BLOCK_N / CH;
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_tiles = smem_base;
+  const uint32_t smem_slabs = smem_base + kStages * Cfg::kStageBytes;
+  const uint32_t smem_bars = smem_slabs + Cfg::kSlabTotal;
+  auto full_bar = [&](int s) { return smem_bars + 8u * s; };
+  auto empty_bar = [&](int s) { return smem_bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return smem_bars + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return smem_bars + 8u * (2 * kStages + kAccStages + s); };
+  auto res_bar = [&](int w, int b) {
+    return smem_bars + 8u * (2 * kStages + 2 * kAccStages + w * kSlabBufs + b);
+  };
+  const uint32_t tmem_ptr_smem = smem_bars + 8u * Cfg::kNumBarriers;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of smem_base
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_c);
+    if (p.has_res) prefetch_tmap(&tmap_r);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kNumEpiWarps);
+    }
+    for (int w = 0; w < kNumEpiWarps; ++w)
+      for (int b = 0; b < kSlabBufs; ++b) mbar_init(res_bar(w, b), 1);
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base =
+      *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+  const int num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
+
+  if (warp_idx == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t / num_n_tiles, n_blk = t % num_n_tiles;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_tiles + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * BLOCK_N);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_tiles + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // +32 bytes per UMMA_K step inside the swizzle span -> +2 in the (addr>>4) field
+            umma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                         (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(empty_bar(stage));                      // frees the smem slot
+          if (kb == num_k_blocks - 1) umma_commit(tfull_bar(acc));  // accumulator ready
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else {
+    // -------------------------------- epilogue --------------------------------
+    const int q = warp_idx & 3;          // TMEM lane quarter this warp may access
+    const int ew = warp_idx - 2;         // slab owner index 0..3
+    const uint32_t slab0 = smem_slabs + (uint32_t)(ew * kSlabBufs) * kSlabBytes;
+    uint8_t* slab0_gen = smem_gen + (slab0 - smem_base);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t cc = 0;  // running chunk counter (selects slab buffer + residual barrier parity)
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / num_n_tiles, n_blk = t % num_n_tiles;
+      const int row0 = m_blk * kBlockM + q * 32;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_acc = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        const int n0 = n_blk * BLOCK_N + c * CH;
+        if (n0 >= p.N) break;
+        const int buf = (int)(cc & 1u);
+        const uint32_t slab = slab0 + (uint32_t)buf * kSlabBytes;
+        uint8_t* slab_gen = slab0_gen + buf * kSlabBytes;
+        // The store that last read this buffer was issued two chunks ago.
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        if (p.has_res && lane == 0) {
+          mbar_expect_tx(res_bar(ew, buf), kSlabBytes);
+          tma_load_2d(slab, &tmap_r, res_bar(ew, buf), n0, row0);
+        }
+        float v[CH];
+        {
+          uint32_t r[32];
+#pragma unroll
+          for (int h = 0; h < CH / 32; ++h) {
+            tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * CH + h * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[h * 32 + j] = __uint_as_float(r[j]);
+          }
+        }
+        if (c == NCH - 1 || n0 + CH >= p.N) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        const bool full_chunk = (n0 + CH <= p.N);
+        if (p.bias != nullptr) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
+          }
+        }
+        if (p.act != kActNone) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = apply_act<false>(v[j], p.act);
+        }
+        if (p.gamma != nullptr) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j));
+              v[j] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n0 + j < p.N) v[j] *= __ldg(p.gamma + n0 + j);
+          }
+        }
+        // slab row = lane; 16-byte chunk j lives at ((j ^ (lane & 7)) << 4) (TMA SWIZZLE_128B)
+        uint8_t* my_row = slab_gen + lane * 128;
+        const int sw = lane & 7;
+        if (p.has_res) {
+          mbar_wait(res_bar(ew, buf), (cc >> 1) & 1u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
+            if constexpr (sizeof(OutT) == 2) {
+              float2 f;
+              f = unpack_bf16x2(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+              f = unpack_bf16x2(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+              f = unpack_bf16x2(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+              f = unpack_bf16x2(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+            } else {
+              v[4 * j + 0] += __uint_as_float(u.x);
+              v[4 * j + 1] += __uint_as_float(u.y);
+              v[4 * j + 2] += __uint_as_float(u.z);
+              v[4 * j + 3] += __uint_as_float(u.w);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 u;
+          if constexpr (sizeof(OutT) == 2) {
+            u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          } else {
+            u.x = __float_as_uint(v[4 * j + 0]);
+            u.y = __float_as_uint(v[4 * j + 1]);
+            u.z = __float_as_uint(v[4 * j + 2]);
+            u.w = __float_as_uint(v[4 * j + 3]);
+          }
+          *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = u;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_c, slab, n0, row0);
+          tma_store_commit();
+        }
+        ++cc;
+      }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------ host side -----------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+  });
+  return fn;
+}
+
+// 2D row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols].
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint64_t cols,
+                 uint64_t ld, uint32_t box_rows, uint32_t box_cols, const char* what) {
+  auto encode = get_encode_fn();
+  if (encode == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return kCudaError;
+  }
+  const uint64_t esize = dtype == kBF16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || ((ld * esize) & 15u) != 0) {
+    set_last_error("gemm: %s must be 16-byte aligned with a 16-byte multiple row pitch (ptr=%p ld=%llu)",
+                   what, ptr, (unsigned long long)ld);
+    return kInvalidArgument;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * esize};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                      2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)",
+                   what, (int)r, (unsigned long long)rows, (unsigned long long)cols,
+                   (unsigned long long)ld, box_rows, box_cols);
+    return kCudaError;
+  }
+  return kOk;
+}
+
+template <int BLOCK_N, typename OutT>
+int launch_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
+                const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act,
+                cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int out_dtype = sizeof(OutT) == 2 ? kBF16 : kF32;
+  constexpr int CH = 128 / (int)sizeof(OutT);
+  CUtensorMap ta, tb, tc, tr;
+  int st;
+  if ((st = make_tmap_2d(&ta, A, kBF16, M, K, lda, kBlockM, kBlockK, "A")) != kOk) return st;
+  if ((st = make_tmap_2d(&tb, W, kBF16, N, K, ldw, BLOCK_N, kBlockK, "W")) != kOk) return st;
+  if ((st = make_tmap_2d(&tc, C, out_dtype, M, N, ldc, 32, CH, "C")) != kOk) return st;
+  if (residual != nullptr) {
+    if ((st = make_tmap_2d(&tr, residual, out_dtype, M, N, ldr, 32, CH, "residual")) != kOk) return st;
+  } else {
+    tr = tc;
+  }
+  auto kernel = gemm_bf16_tcgen05_kernel<BLOCK_N, OutT>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  GemmParams p{M, N, K, bias, gamma, act, residual != nullptr ? 1 : 0};
+  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kernel<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, p);
+  TFIMM_LAUNCH_OK("gemm_bf16_tcgen05_kernel");
+  return kOk;
+}
+
+int pick_block_n(int M, int N) {
+  const int sms = sm_count();
+  const int mt = (M + kBlockM - 1) / kBlockM;
+  int best = 256;
+  double best_cost = 1e30;
+  for (int bn : {256, 128, 64}) {
+    const int nt = (N + bn - 1) / bn;
+    const long tiles = (long)mt * nt;
+    const long waves = (tiles + sms - 1) / sms;
+    // time ~ waves * per-tile MMA time (prop. to bn); small preference for wide tiles
+    const double cost = (double)waves * bn * (bn == 256 ? 1.0 : (bn == 128 ? 1.04 : 1.10));
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace
+
+int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const float* bias,
+                       const float* gamma, const void* residual, int ldr, void* C, int ldc, int M,
+                       int N, int K, int act, int out_dtype, int force_block_n, cudaStream_t stream) {
+  TFIMM_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: M, N, K must be positive (got %d %d %d)", M, N, K);
+  TFIMM_CHECK_ARG(out_dtype == kBF16 || out_dtype == kF32, "gemm: out_dtype must be bf16 or f32");
+  TFIMM_CHECK_ARG(K % 8 == 0, "gemm: K must be a multiple of 8 (got %d)", K);
+  TFIMM_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0, "gemm: bias must be 16-byte aligned");
+  TFIMM_CHECK_ARG(gamma == nullptr || (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0, "gemm: gamma must be 16-byte aligned");
+  const int bn = force_block_n > 0 ? force_block_n : pick_block_n(M, N);
+#define TFIMM_GEMM_CASE(BN)                                                                           \
+  case BN:                                                                                            \
+    return out_dtype == kBF16                                                                         \
+               ? launch_gemm<BN, __nv_bfloat16>(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, \
+                                                N, K, act, stream)                                    \
+               : launch_gemm<BN, float>(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K,   \
+                                        act, stream);
+  switch (bn) {
+    TFIMM_GEMM_CASE(256)
+    TFIMM_GEMM_CASE(128)
+    TFIMM_GEMM_CASE(64)
+    default:
+      set_last_error("gemm: unsupported block_n %d", bn);
+      return kInvalidArgument;
+  }
+#undef TFIMM_GEMM_CASE
+}
+
+}  // namespace tfimm

@@ -1,0 +1,165 @@
+"""Tensor-level launchers: torch CUDA tensors in, kernel launches on torch's current stream.
+
+torch is used for device memory and stream handles only; every function here ends in exactly
+one call into ``libtfimm_b200.so``.  Nothing falls back to torch ops.
+"""
+from typing import Optional
+
+import torch
+
+from . import lib as _lib
+
+F32, BF16, U8 = _lib.F32, _lib.BF16, _lib.U8
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8}
+
+# number of kernels launched through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"tfimm_b200 kernels take float32 / bfloat16 / uint8 tensors, got {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.KernelLibraryError(
+                "tfimm_b200 kernels only run on CUDA tensors (there is no CPU fallback)."
+            )
+
+
+def _call(name, *args):
+    global launch_count
+    fn = getattr(_lib.load(), name)
+    _lib.check(fn(*args), name)
+    launch_count += 1
+
+
+def act_code(act) -> int:
+    try:
+        return _lib.ACT[act]
+    except KeyError:
+        raise ValueError(f"Unknown activation: {act}.")
+
+
+def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dtype=None, block_n=0):
+    """out = residual + gamma * act(a @ w.T + bias).  a:(M,K), w:(N,K); bf16 -> tcgen05, fp32 -> SIMT."""
+    _cuda(a, w, bias, gamma, residual, out)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (a.shape, w.shape)
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out_dtype = out_dtype or (residual.dtype if residual is not None else a.dtype)
+        ldc = (N + 7) // 8 * 8
+        buf = torch.empty((M, ldc), device=a.device, dtype=out_dtype)
+        out = buf[:, :N] if ldc != N else buf
+    assert out.shape == (M, N) and out.stride(1) == 1
+    if residual is not None:
+        assert residual.shape == (M, N) and residual.dtype == out.dtype and residual.stride(1) == 1
+    ldr = residual.stride(0) if residual is not None else 0
+    if a.dtype == torch.bfloat16:
+        assert w.dtype == torch.bfloat16
+        _call("tfimm_b200_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+              _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
+              _code(out), block_n, _stream())
+    else:
+        assert a.dtype == torch.float32 and w.dtype == torch.float32 and out.dtype == torch.float32
+        _call("tfimm_b200_gemm_f32", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+              _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
+              _stream())
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out_dtype, out=None):
+    """LayerNorm over the last axis of a 2D (possibly row-strided) tensor."""
+    _cuda(x, gamma, beta, out)
+    rows, C = x.shape
+    assert x.stride(1) == 1
+    if out is None:
+        out = torch.empty((rows, C), device=x.device, dtype=out_dtype)
+    _call("tfimm_b200_layernorm", x.data_ptr(), _code(x), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
+          out.data_ptr(), _code(out), out.stride(0), rows, C, float(eps), _stream())
+    return out
+
+
+def layernorm_patch2x2(x, gamma, beta, eps, out_dtype):
+    """x: (B,H,W,C) contiguous -> (B*H/2*W/2, 4C) LN'd pixels in 2x2/stride-2 im2col order."""
+    _cuda(x, gamma, beta)
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((B * (H // 2) * (W // 2), 4 * C), device=x.device, dtype=out_dtype)
+    _call("tfimm_b200_layernorm_patch2x2", x.data_ptr(), _code(x), gamma.data_ptr(), beta.data_ptr(),
+          out.data_ptr(), _code(out), B, H, W, C, float(eps), _stream())
+    return out
+
+
+def patch_merge_ln(x, gamma, beta, eps, out_dtype):
+    """Swin PatchMerging gather + LN.  x: (B,H,W,C) contiguous -> (B*H/2*W/2, 4C)."""
+    _cuda(x, gamma, beta)
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((B * (H // 2) * (W // 2), 4 * C), device=x.device, dtype=out_dtype)
+    _call("tfimm_b200_patch_merge_ln", x.data_ptr(), _code(x), gamma.data_ptr(), beta.data_ptr(),
+          out.data_ptr(), _code(out), B, H, W, C, float(eps), _stream())
+    return out
+
+
+def attention(qkv, B, N, H, dh, scale, bias=None, mask=None, probs=None):
+    """softmax(scale q k^T [+bias +mask]) v from packed qkv (B*N, 3*H*dh) -> (B*N, H*dh)."""
+    _cuda(qkv, bias, mask, probs)
+    assert qkv.shape == (B * N, 3 * H * dh) and qkv.is_contiguous()
+    out = torch.empty((B * N, H * dh), device=qkv.device, dtype=qkv.dtype)
+    if qkv.dtype == torch.bfloat16 and bias is None and mask is None and probs is None:
+        _call("tfimm_b200_attention_bf16", qkv.data_ptr(), out.data_ptr(), B, N, H, dh, float(scale), _stream())
+    elif qkv.dtype == torch.float32:
+        nmask = mask.shape[0] if mask is not None else 1
+        _call("tfimm_b200_attention_f32", qkv.data_ptr(), out.data_ptr(), _ptr(bias), _ptr(mask), nmask, B, N,
+              H, dh, float(scale), _ptr(probs), _stream())
+    else:
+        raise _lib.KernelLibraryError("attention: unsupported dtype / option combination")
+    return out
+
+
+def patchify(img, p, out_dtype, mean=None, inv_std=None, scale=1.0):
+    """img: (B,H,W,C) -> (B*H/p*W/p, ceil8(p*p*C)); optional fused (x*scale-mean)*inv_std."""
+    _cuda(img, mean, inv_std)
+    B, H, W, C = img.shape
+    assert img.is_contiguous()
+    K = p * p * C
+    Kpad = (K + 7) // 8 * 8
+    out = torch.empty((B * (H // p) * (W // p), Kpad), device=img.device, dtype=out_dtype)
+    _call("tfimm_b200_patchify", img.data_ptr(), _code(img), out.data_ptr(), _code(out), B, H, W, C, p, Kpad,
+          float(scale), _ptr(mean), _ptr(inv_std), _stream())
+    return out
+
+
+def assemble_tokens(patches, cls, dist, pos, B, P, out_dtype):
+    _cuda(patches, cls, dist, pos)
+    D = patches.shape[1]
+    ntok = 2 if dist is not None else 1
+    out = torch.empty((B * (P + ntok), D), device=patches.device, dtype=out_dtype)
+    _call("tfimm_b200_assemble_tokens", patches.data_ptr(), _code(patches), cls.data_ptr(), _ptr(dist),
+          pos.data_ptr(), out.data_ptr(), _code(out), B, P, ntok, D, _stream())
+    return out
+
+
+def cast(x, dtype):
+    _cuda(x)
+    if x.dtype == dtype:
+        return x
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    _call("tfimm_b200_cast", x.data_ptr(), _code(x), out.data_ptr(), _code(out), x.numel(), _stream())
+    return out

@@ -1,0 +1,244 @@
+"""Base class of every engine model: owns the weights, mirrors the reference's model-object contract.
+
+Contract kept from the reference (e.g. tfimm/architectures/vit.py:298-478):
+  * constructor takes the config object (or a dict of its fields, the ``keras_serializable``
+    convention, tfimm/models/serialization.py:50-70) and an optional ``name``
+  * ``model(x, training=False, return_features=False)`` -> logits, or ``(logits, features)``
+  * ``forward_features``, ``cfg``, ``name``, ``dummy_inputs``, ``feature_names``
+  * ``model.weights``: objects with ``.name`` (``"<model name>/<path>:0"``), ``.shape``,
+    ``.numpy()``; names and layouts are the reference's TF variable names and layouts, so a
+    flat ``{path: array}`` dict converted by the reference's own rules loads unchanged.
+
+What is different by design: weights live in HBM as torch CUDA tensors; the forward pass is a
+sequence of hand-written sm_100a kernels (tfimm.backend.ops); inference only.
+"""
+import math
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ..backend import lib as _lib
+
+
+@dataclass(frozen=True)
+class ParamSpec:
+    shape: Tuple[int, ...]
+    init: str = "zeros"  # zeros | ones | glorot_uniform | const:<v> | normal:<std> | uniform:<a>
+    trainable: bool = True
+
+
+class Weight:
+    """Read/write view of one model parameter under its reference (TF) variable name."""
+
+    def __init__(self, model: "Model", key: str):
+        self._model = model
+        self.key = key
+
+    @property
+    def name(self) -> str:
+        return f"{self._model.name}/{self.key}:0"
+
+    @property
+    def shape(self):
+        return tuple(self._model.params[self.key].shape)
+
+    @property
+    def trainable(self) -> bool:
+        return self._model.param_specs()[self.key].trainable
+
+    def numpy(self) -> np.ndarray:
+        return self._model.params[self.key].detach().float().cpu().numpy()
+
+    def assign(self, value):
+        self._model.load_weights_dict({self.key: value}, strict=False)
+
+    def __repr__(self):
+        return f"<Weight {self.name} shape={self.shape}>"
+
+
+def _init_tensor(spec: ParamSpec, gen: torch.Generator) -> torch.Tensor:
+    shape = tuple(spec.shape)
+    kind, _, arg = spec.init.partition(":")
+    if kind == "zeros":
+        return torch.zeros(shape)
+    if kind == "ones":
+        return torch.ones(shape)
+    if kind == "const":
+        return torch.full(shape, float(arg))
+    if kind == "normal":
+        return torch.randn(shape, generator=gen) * float(arg)
+    if kind == "uniform":
+        a = float(arg)
+        return (torch.rand(shape, generator=gen) * 2 - 1) * a
+    if kind == "glorot_uniform":
+        # Keras default for Dense / Conv kernels: receptive field * in, receptive field * out
+        rf = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+        fan_in = shape[-2] * rf if len(shape) >= 2 else shape[0]
+        fan_out = shape[-1] * rf if len(shape) >= 2 else shape[0]
+        limit = math.sqrt(6.0 / (fan_in + fan_out))
+        return (torch.rand(shape, generator=gen) * 2 - 1) * limit
+    raise ValueError(f"Unknown initializer {spec.init}")
+
+
+class Model:
+    cfg_class = None
+    # regexes of weights created at build time that need not be present when loading
+    keys_to_ignore_on_load_missing: List[str] = []
+
+    def __init__(self, cfg, *args, name: Optional[str] = None, precision: str = "bf16",
+                 device=None, seed: int = 0, **kwargs):
+        if isinstance(cfg, dict):
+            cfg = self.cfg_class(**cfg)
+        if self.cfg_class is not None and not isinstance(cfg, self.cfg_class):
+            raise ValueError("Must pass either `cfg` (ModelConfig) or `cfg` (dict)")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.cfg = cfg
+        self.name = name or cfg.name
+        self.precision = precision
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
+        self.params: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        self._specs = None
+        self._plan = None  # engine-layout tensors derived from params (see _compile)
+        self._seed = seed
+        self._build()
+
+    # ------------------------------------------------------------------ parameters
+    def param_specs(self) -> "OrderedDict[str, ParamSpec]":
+        if self._specs is None:
+            self._specs = self._param_specs()
+        return self._specs
+
+    def _param_specs(self) -> "OrderedDict[str, ParamSpec]":
+        raise NotImplementedError
+
+    def _build(self):
+        gen = torch.Generator().manual_seed(self._seed)
+        for key, spec in self.param_specs().items():
+            self.params[key] = _init_tensor(spec, gen).to(self.device)
+        self._plan = None
+
+    @property
+    def weights(self) -> List[Weight]:
+        return [Weight(self, k) for k in self.params]
+
+    @property
+    def trainable_weights(self) -> List[Weight]:
+        return [w for w in self.weights if w.trainable]
+
+    def count_params(self) -> int:
+        return int(sum(p.numel() for p in self.params.values()))
+
+    def weights_dict(self) -> Dict[str, np.ndarray]:
+        """Flat ``{path: fp32 array}`` in reference (TF) names and layouts."""
+        return {k: v.detach().float().cpu().numpy() for k, v in self.params.items()}
+
+    def load_weights_dict(self, weights: Dict[str, object], strict: bool = True):
+        """Loads reference-layout weights.  ``strict``: every parameter of the model must be given
+        (except ``keys_to_ignore_on_load_missing``) and no unknown key may be present."""
+        import re
+
+        missing = []
+        for key, cur in self.params.items():
+            if key not in weights:
+                if strict and not any(re.search(p, key) for p in self.keys_to_ignore_on_load_missing):
+                    missing.append(key)
+                continue
+            val = weights[key]
+            val = val.detach().cpu() if isinstance(val, torch.Tensor) else torch.from_numpy(np.asarray(val))
+            val = val.to(torch.float32)
+            if tuple(val.shape) != tuple(cur.shape):
+                raise ValueError(f"Shape mismatch for {key}: model {tuple(cur.shape)}, given {tuple(val.shape)}")
+            self.params[key] = val.contiguous().to(self.device)
+        if strict:
+            unknown = [k for k in weights if k not in self.params]
+            if missing or unknown:
+                raise AttributeError(f"load_weights_dict: missing={missing[:5]} unknown={unknown[:5]}")
+        self._plan = None
+
+    def to(self, device):
+        self.device = torch.device(device)
+        for k in self.params:
+            self.params[k] = self.params[k].to(self.device)
+        self._plan = None
+        return self
+
+    # ------------------------------------------------------------------ engine helpers
+    @property
+    def act_dtype(self) -> torch.dtype:
+        return torch.bfloat16 if self.precision == "bf16" else torch.float32
+
+    def _dense_weight(self, key: str, pad_k_to: int = 8) -> torch.Tensor:
+        """TF Dense/Conv kernel ``(..., in, out)`` -> engine layout ``W[out][K]`` (K contiguous,
+        K = prod(leading dims), zero-padded to a multiple of ``pad_k_to``), in the activation dtype."""
+        w = self.params[key]
+        out = w.shape[-1]
+        w2 = w.reshape(-1, out).t().contiguous()  # (out, K)
+        K = w2.shape[1]
+        Kpad = (K + pad_k_to - 1) // pad_k_to * pad_k_to
+        if Kpad != K:
+            w2 = torch.nn.functional.pad(w2, (0, Kpad - K))
+        return w2.to(self.act_dtype).contiguous()
+
+    def _vec(self, key: str) -> torch.Tensor:
+        return self.params[key].reshape(-1).float().contiguous()
+
+    def _compile(self):
+        raise NotImplementedError
+
+    def _ensure_plan(self):
+        if self.device.type != "cuda":
+            raise _lib.KernelLibraryError(
+                "tfimm_b200 models only run on a CUDA device (sm_100a); there is no CPU fallback. "
+                "The model was created on device '%s'." % self.device
+            )
+        if self._plan is None:
+            _lib.load()
+            self._plan = self._compile()
+        return self._plan
+
+    def _input(self, x) -> torch.Tensor:
+        if not isinstance(x, torch.Tensor):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if x.dim() == 3:
+            x = x[None]
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        if self.precision == "fp32" and x.dtype != torch.float32:
+            x = x.float()
+        return x.to(self.device, non_blocking=True).contiguous()
+
+    # ------------------------------------------------------------------ public forward API
+    @property
+    def dummy_inputs(self) -> torch.Tensor:
+        return torch.zeros((1, *self.cfg.input_size, self.cfg.in_channels), device=self.device)
+
+    @property
+    def feature_names(self) -> List[str]:
+        _, features = self(self.dummy_inputs, return_features=True)
+        return list(features.keys())
+
+    def forward_features(self, x, training=False, return_features=False):
+        raise NotImplementedError
+
+    def call(self, x, training=False, return_features=False):
+        raise NotImplementedError
+
+    def __call__(self, x, training=False, return_features=False):
+        if training:
+            raise NotImplementedError("tfimm_b200 is an inference engine: training=True is not supported.")
+        return self.call(x, training=False, return_features=return_features)
+
+    def get_config(self):
+        import dataclasses
+
+        return dataclasses.asdict(self.cfg)
+
+    @classmethod
+    def from_config(cls, config):
+        return cls(config)

@@ -1,0 +1,6 @@
+"""Normalisation constants (values as in the reference's tfimm/utils/constants.py:3-6;
+they apply to pixel values already scaled to [0, 1])."""
+IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
+IMAGENET_INCEPTION_MEAN = (0.5, 0.5, 0.5)
+IMAGENET_INCEPTION_STD = (0.5, 0.5, 0.5)

@@ -1,0 +1,263 @@
+"""GPU kernel numerics: every CUDA kernel against a plain PyTorch fp32 statement of the same op.
+
+All calls go through the C ABI (ctypes -> libtfimm_b200.so).  Tolerances are written next to
+each comparison: bf16 kernels are compared with fp32 references computed from the SAME
+bf16-rounded inputs, so the only differences are accumulation order and output rounding.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from tfimm.backend import ops
+
+    return ops
+
+
+def _act_ref(x, act):
+    if act in (None, "linear"):
+        return x
+    if act == "gelu":
+        return torch.nn.functional.gelu(x)  # exact erf
+    if act == "swish":
+        return x * torch.sigmoid(x)
+    if act == "relu":
+        return torch.relu(x)
+    if act == "relu6":
+        return torch.clamp(x, 0, 6)
+    if act == "tanh":
+        return torch.tanh(x)
+    if act == "sigmoid":
+        return torch.sigmoid(x)
+    raise ValueError(act)
+
+
+GEMM_SHAPES = [
+    # M, N, K
+    (128, 256, 64),
+    (128, 256, 768),
+    (256, 768, 768),
+    (394, 2304, 768),     # M tail, several N tiles
+    (1000, 1000, 1024),   # N tail (classifier head), M tail
+    (50432 // 8, 3072, 768),
+    (640, 24, 48),        # EfficientNet-like tiny N / K tail
+    (512, 56, 336),
+    (300, 384, 128),
+    (77, 1000, 192),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_bf16_plain(M, N, K, out_dtype):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = ops.gemm(a, w, bias=bias, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    err = (out.float() - ref).abs().max().item()
+    # fp32 out: accumulation-order noise only; bf16 out: one rounding (2^-9 relative)
+    tol = 2e-3 if out_dtype == torch.float32 else 2e-2 + 4e-3 * ref.abs().max().item()
+    assert err < tol, (err, tol)
+
+
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+@pytest.mark.parametrize("act", [None, "gelu", "swish", "relu", "relu6", "tanh", "sigmoid"])
+def test_gemm_bf16_epilogues(block_n, act):
+    ops = _ops()
+    M, N, K = 777, 520, 264
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    gamma = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    out = ops.gemm(a, w, bias=bias, act=act, gamma=gamma, residual=res, out_dtype=torch.float32, block_n=block_n)
+    torch.cuda.synchronize()
+    ref = res + gamma * _act_ref(a.float() @ w.float().t() + bias, act)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3, err
+
+
+def test_gemm_bf16_inplace_residual_bf16():
+    ops = _ops()
+    M, N, K = 1024, 768, 3072
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    ref = x.float() + a.float() @ w.float().t() + bias
+    ops.gemm(a, w, bias=bias, residual=x, out=x)
+    torch.cuda.synchronize()
+    err = (x.float() - ref).abs().max().item()
+    assert err < 2e-2 + 4e-3 * ref.abs().max().item(), err
+
+
+def test_gemm_bf16_strided_a():
+    """A given as a row-strided view (e.g. token 0 of every image)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    full = torch.randn(64, 5, 256, device="cuda", generator=g).to(torch.bfloat16)
+    a = full[:, 0, :]
+    w = (torch.randn(100, 256, device="cuda", generator=g) / 16).to(torch.bfloat16)
+    out = ops.gemm(a, w, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    assert (out - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("act", [None, "gelu", "swish"])
+def test_gemm_f32(act):
+    ops = _ops()
+    M, N, K = 300, 200, 136
+    g = torch.Generator(device="cuda").manual_seed(4)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    bias = torch.randn(N, device="cuda", generator=g)
+    gamma = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    out = ops.gemm(a, w, bias=bias, act=act, gamma=gamma, residual=res)
+    torch.cuda.synchronize()
+    ref = res + gamma * _act_ref((a.double() @ w.double().t()).float() + bias, act)
+    assert (out - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("C", [32, 192, 768, 1024, 4096])
+@pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16),
+                                                (torch.float32, torch.float32)])
+def test_layernorm(C, in_dtype, out_dtype):
+    ops = _ops()
+    rows = 1003
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = (torch.randn(rows, C, device="cuda", generator=g) * 3 + 1.5).to(in_dtype)
+    gamma = torch.randn(C, device="cuda", generator=g)
+    beta = torch.randn(C, device="cuda", generator=g)
+    out = ops.layernorm(x, gamma, beta, 1e-6, out_dtype)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-6)
+    # bf16 output: one rounding, 2^-9 relative to the element's magnitude
+    tol = 1e-4 if out_dtype == torch.float32 else 2.0 ** -8 * ref.abs().max().item() + 1e-3
+    assert (out.float() - ref).abs().max().item() < tol
+
+
+def test_layernorm_strided_rows():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(16, 197, 768, device="cuda", generator=g)
+    gamma = torch.randn(768, device="cuda", generator=g)
+    beta = torch.randn(768, device="cuda", generator=g)
+    out = ops.layernorm(x[:, 0, :], gamma, beta, 1e-6, torch.float32)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x[:, 0, :], (768,), gamma, beta, 1e-6)
+    assert (out - ref).abs().max().item() < 1e-4
+
+
+def test_layernorm_patch2x2_and_patch_merge():
+    ops = _ops()
+    B, H, W, C = 3, 8, 12, 64
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g)
+    gamma = torch.randn(C, device="cuda", generator=g)
+    beta = torch.randn(C, device="cuda", generator=g)
+    out = ops.layernorm_patch2x2(x, gamma, beta, 1e-6, torch.float32)
+    ln = torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-6)
+    ref = ln.view(B, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * H // 2 * W // 2, 4 * C)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() < 1e-4
+    # Swin patch merging: (0,0),(1,0),(0,1),(1,1) then LN over 4C
+    g4 = torch.randn(4 * C, device="cuda", generator=g)
+    b4 = torch.randn(4 * C, device="cuda", generator=g)
+    out = ops.patch_merge_ln(x, g4, b4, 1e-5, torch.float32)
+    cat = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], dim=-1)
+    ref = torch.nn.functional.layer_norm(cat, (4 * C,), g4, b4, 1e-5).reshape(-1, 4 * C)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() < 1e-4
+
+
+def _attn_ref(qkv, B, N, H, dh, scale, bias=None, mask=None):
+    q, k, v = qkv.float().view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
+    s = scale * q @ k.transpose(-1, -2)
+    if bias is not None:
+        s = s + bias[None]
+    if mask is not None:
+        nm = mask.shape[0]
+        s = (s.view(B // nm, nm, H, N, N) + mask[None, :, None]).view(B, H, N, N)
+    p = torch.softmax(s, dim=-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(B * N, H * dh)
+    return o, p
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 197, 12), (3, 5, 2), (1, 65, 3), (2, 128, 4), (1, 224, 2), (1, 577, 2), (2, 17, 1)])
+def test_attention_bf16(B, N, H):
+    ops = _ops()
+    dh = 64
+    g = torch.Generator(device="cuda").manual_seed(N)
+    qkv = (torch.randn(B * N, 3 * H * dh, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    out = ops.attention(qkv, B, N, H, dh, dh ** -0.5)
+    torch.cuda.synchronize()
+    ref, _ = _attn_ref(qkv, B, N, H, dh, dh ** -0.5)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2, err   # P is rounded to bf16 before the PV product; output rounded to bf16
+
+
+def test_attention_f32_with_bias_mask_probs():
+    ops = _ops()
+    B, N, H, dh = 8, 49, 4, 32
+    g = torch.Generator(device="cuda").manual_seed(9)
+    qkv = torch.randn(B * N, 3 * H * dh, device="cuda", generator=g)
+    bias = torch.randn(H, N, N, device="cuda", generator=g)
+    mask = torch.where(torch.rand(4, N, N, device="cuda", generator=g) > 0.7, -100.0, 0.0)
+    probs = torch.empty(B, H, N, N, device="cuda")
+    out = ops.attention(qkv, B, N, H, dh, dh ** -0.5, bias=bias, mask=mask, probs=probs)
+    torch.cuda.synchronize()
+    ref, p = _attn_ref(qkv, B, N, H, dh, dh ** -0.5, bias, mask)
+    assert (out - ref).abs().max().item() < 2e-5
+    assert (probs - p).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("p,C,H,W", [(16, 3, 224, 224), (4, 3, 64, 96), (2, 3, 32, 32), (2, 64, 8, 8), (8, 1, 32, 32)])
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.uint8])
+def test_patchify(p, C, H, W, in_dtype):
+    ops = _ops()
+    B = 2
+    g = torch.Generator(device="cuda").manual_seed(p * C)
+    if in_dtype == torch.uint8:
+        img = torch.randint(0, 256, (B, H, W, C), device="cuda", generator=g, dtype=torch.uint8)
+        mean = torch.tensor([0.485, 0.456, 0.406] * 22, device="cuda")[:C].contiguous()
+        std = torch.tensor([0.229, 0.224, 0.225] * 22, device="cuda")[:C].contiguous()
+        out = ops.patchify(img, p, torch.float32, mean=mean, inv_std=1.0 / std, scale=1.0 / 255.0)
+        imgf = (img.float() / 255.0 - mean) / std
+    else:
+        img = torch.randn(B, H, W, C, device="cuda", generator=g)
+        out = ops.patchify(img, p, torch.float32)
+        imgf = img
+    torch.cuda.synchronize()
+    K = p * p * C
+    ref = imgf.view(B, H // p, p, W // p, p, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, K)
+    assert out.shape[1] == (K + 7) // 8 * 8
+    assert (out[:, :K] - ref).abs().max().item() < 1e-5
+    assert out[:, K:].abs().max().item() == 0 if out.shape[1] > K else True
+
+
+def test_assemble_tokens():
+    ops = _ops()
+    B, P, D = 3, 16, 64
+    g = torch.Generator(device="cuda").manual_seed(11)
+    patches = torch.randn(B * P, D, device="cuda", generator=g).to(torch.bfloat16)
+    cls = torch.randn(D, device="cuda", generator=g)
+    dist = torch.randn(D, device="cuda", generator=g)
+    for d, ntok in ((None, 1), (dist, 2)):
+        pos = torch.randn(P + ntok, D, device="cuda", generator=g)
+        out = ops.assemble_tokens(patches, cls, d, pos, B, P, torch.float32)
+        torch.cuda.synchronize()
+        toks = [cls[None, None].expand(B, 1, D)] + ([d[None, None].expand(B, 1, D)] if d is not None else [])
+        ref = torch.cat(toks + [patches.float().view(B, P, D)], dim=1) + pos[None]
+        assert (out.view(B, P + ntok, D) - ref).abs().max().item() < 1e-6
