@@ -1,0 +1,364 @@
+"""Headline benchmark: forward images/sec of a tfimm classifier on N B200 GPUs (one node).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model vit_base_patch16_224]
+                    [--batch 256] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward pass of the model over one synthetic batch (``--batch`` images per GPU,
+224x224x3 unless the model's native size differs; weak scaling: per-GPU batch fixed).  Rank 0
+prints ONE JSON line (see the task contract): whole-job images/sec with inputs resident in HBM
+(``value``), the same through the public API from pinned host memory (``e2e``), the roofline of
+the dominant kernel family measured live with CUDA events, the CPU oracle timed beside it, and the
+SM clocks sampled during the timed region.
+
+``--impl reference`` times the CPU stand-in for the reference (the torch-CPU oracle restatement;
+TensorFlow is not installed in this image) on the same config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "tensorflow-image-models_b200"))
+sys.path.insert(0, str(ROOT))
+
+METRIC = "images/sec fwd bs=256 224px"
+# Algorithmic work per image: GFLOP and op-level HBM MB in bf16
+WORK = {
+    "vit_base_patch16_224": {"gflop": 35.13, "mb": 80.5, "bound": "tensor"},
+    "vit_tiny_patch16_224": {"gflop": 2.51, "mb": 20.3, "bound": "tensor"},
+    "convnext_base": {"gflop": 30.71, "mb": 124.6, "bound": "hbm"},
+    "swin_base_patch4_window7_224": {"gflop": 30.86, "mb": 140.2, "bound": "hbm"},
+    "efficientnet_b4": {"gflop": 8.79, "mb": 322.5, "bound": "hbm"},
+}
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _input_hw(cfg):
+    return tuple(cfg.input_size)
+
+
+def _oracle_forward(model_name):
+    import importlib
+
+    import tfimm
+
+    cfg = tfimm.models.model_config(model_name)
+    fam = {"ViT": "vit", "SwinTransformer": "swin", "ConvNeXt": "convnext", "EfficientNet": "efficientnet",
+           "ResNet": "resnet"}[tfimm.models.model_class(model_name).__name__]
+    mod = importlib.import_module(f"oracle.{fam}")
+    return cfg, mod
+
+
+def cpu_oracle_throughput(model_name, batch, iters, warmup=1):
+    """images/sec of the torch-CPU oracle (the reference's CPU stand-in) on all host cores."""
+    import torch
+
+    from oracle import params
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, mod = _oracle_forward(model_name)
+    w = params.random_params(mod.param_shapes(cfg), seed=0)
+    h, wd = _input_hw(cfg)
+    x = params.test_images(batch, h, wd, cfg.in_channels)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + iters):
+            t0 = time.perf_counter()
+            mod.forward(cfg, w, x)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    med = statistics.median(times)
+    return {"value": batch / med, "unit": "images/sec", "cores": cores, "kind": "port",
+            "sample": f"{model_name} fp32 forward, batch {batch}, median of {iters} after {warmup} warm-up "
+                      f"(torch-CPU oracle restatement; TensorFlow is not installed)",
+            "ms_per_step": med * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.ref_batch
+    res = cpu_oracle_throughput(args.model, batch, max(1, args.steps), max(1, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "images/sec",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} forward, per-GPU batch {args.batch}, 224px NHWC synthetic; "
+                               f"CPU sample batch {batch}"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import tfimm
+    from tfimm.backend import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = tfimm.create_model(args.model, precision="bf16", device=dev, seed=0)
+    # random-init every weight (the reference's zeros/ones initialisers would make parts inert)
+    g = torch.Generator().manual_seed(1234)
+    rnd = {}
+    for k, v in model.params.items():
+        leaf = k.rsplit("/", 1)[-1]
+        if leaf in ("kernel", "depthwise_kernel"):
+            fan_in = int(np.prod(v.shape[:-1]))
+            rnd[k] = torch.randn(v.shape, generator=g) / fan_in ** 0.5
+        elif leaf in ("gamma", "moving_variance"):
+            rnd[k] = 1.0 + 0.1 * torch.rand(v.shape, generator=g)
+        else:
+            rnd[k] = 0.1 * torch.randn(v.shape, generator=g)
+    model.load_weights_dict(rnd, strict=True)
+
+    B = args.batch
+    h, w = _input_hw(model.cfg)
+    rng = np.random.default_rng(2021 + rank)
+    host = torch.from_numpy(rng.random((B, h, w, model.cfg.in_channels), dtype=np.float32)).pin_memory()
+    x_dev = host.to(dev)
+    nb_classes = model.cfg.nb_classes
+    gathered = torch.empty((world * B, nb_classes), device=dev, dtype=torch.float32) if world > 1 else None
+
+    def step(x):
+        logits = model(x)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, logits.contiguous())
+            return gathered
+        return logits
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---------------- end to end through the public API from pinned host memory ----------------
+    out_host = torch.empty((B, nb_classes), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xd = host.to(dev, non_blocking=True)          # H2D of this step's inputs
+        logits = model(xd)                             # public API call
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, logits.contiguous())
+        out_host.copy_(logits, non_blocking=True)      # D2H of this step's result
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    # ---------------- roofline of the dominant kernel family (live CUDA events) ----------------
+    roof = None
+    if rank == 0:
+        roof = kernel_roofline(model, x_dev, args.model, ops)
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu = cpu_oracle_throughput(args.model, args.ref_batch, 3, 1)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model} forward, per-GPU batch {B}, {h}x{w}x{model.cfg.in_channels} NHWC "
+                                   f"fp32 synthetic images, random-init weights, bf16 operands / fp32 accumulate "
+                                   f"and residual stream",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (154 MB input + >1 GB activations) exceeds the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(model, x_dev, model_name, ops):
+    """Per-kernel-family device time of one forward, measured with CUDA events around every launch
+    (instrumented pass, after the timed region).  Reports the dominant family against its roof."""
+    import torch
+
+    peaks = _peaks()
+    ops.trace = []
+    model(x_dev)
+    torch.cuda.synchronize()
+    trace, ops.trace = ops.trace, None
+    fam = {}
+    for name, e0, e1, flops, nbytes in trace:
+        d = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += flops
+        d["bytes"] += nbytes
+        d["launches"] += 1
+    total_ms = sum(d["ms"] for d in fam.values())
+    top = max(fam, key=lambda k: fam[k]["ms"])
+    d = fam[top]
+    work = WORK.get(model_name)
+    if d["flops"] > 0 and (d["flops"] / max(d["bytes"], 1)) > 100:
+        achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step); "
+                               f"burst {peaks['bf16_tflops']}"}
+    else:
+        achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        peak = peaks["hbm_gbs"]
+        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": f"{peaks['source']} hbm_gbs"}
+    roof["share_of_step"] = d["ms"] / total_ms
+    roof["launches_per_step"] = d["launches"]
+    roof["avg_launch_ms"] = d["ms"] / d["launches"]
+    roof["families_ms"] = {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    if work:
+        B = x_dev.shape[0]
+        roof["model_gflop_per_image"] = work["gflop"]
+        roof["model_mb_per_image"] = work["mb"]
+        roof["model_tensor_frac_instrumented"] = (B * work["gflop"] * 1e9 / (total_ms * 1e-3)) / 1e12 / peaks["bf16_tflops_sustained"]
+    return roof
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--model", default="vit_base_patch16_224")
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=8, help="CPU sample batch for the oracle timing")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,6 +105,25 @@ int tfimm_b200_assemble_tokens(const void* patches, int patch_dtype, const float
                                const float* pos, void* out, int out_dtype, int B, int P, int ntok, int D,
                                void* stream);
 
+/* ZeroPadding2D(k/2) -> DepthwiseConv2D(k x k, stride 1, bias) -> LayerNorm over C (k == 7):
+ * first half of ConvNeXtBlock.call, tfimm/architectures/convnext.py:189-198,219-223.
+ * x:(B,H,W,C) f32|bf16, wgt: fp32 [k*k][C] (= TF depthwise_kernel (k,k,C,1) flattened), out:(B*H*W, C). */
+int tfimm_b200_dwconv_ln(const void* x, int in_dtype, const float* wgt, const float* bias, const float* gamma,
+                         const float* beta, void* out, int out_dtype, int B, int H, int W, int C, int ks,
+                         float eps, void* stream);
+
+/* DepthwiseConv2D(k in {3,5,7}, stride in {1,2}) with explicit top/left zero padding (covers TF "same"
+ * and PadDepthwiseConv2D "symmetric", tfimm/layers/conv.py:91-148) + per-channel bias (folded BatchNorm)
+ * + activation; optional fused squeeze: pool_sum[b][c] += sum over the output pixels (fp32 atomics; the
+ * caller zeroes it and divides by Ho*Wo).  tfimm/architectures/efficientnet_blocks.py:312-323,393-404,241-242. */
+int tfimm_b200_dwconv_bias_act(const void* x, int dtype, const float* wgt, const float* bias, void* out,
+                               float* pool_sum, int B, int H, int W, int C, int ks, int stride, int pad_t,
+                               int pad_l, int Ho, int Wo, int act, void* stream);
+
+/* Mean over the spatial axis: (B, HW, C) -> (B, C) fp32.  GlobalAveragePooling (convnext.py:433,
+ * efficientnet.py:256, swin.py:456, layers/classifier.py:34). */
+int tfimm_b200_global_avg_pool(const void* x, int dtype, float* out, int B, int HW, int C, void* stream);
+
 /* Elementwise dtype conversion. */
 int tfimm_b200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream);
 

@@ -57,6 +57,11 @@ int patchify(const void*, int, void*, int, int, int, int, int, int, int, float, 
 int assemble_tokens(const void*, int, const float*, const float*, const float*, void*, int, int, int, int, int,
                     cudaStream_t);
 int cast_tensor(const void*, int, void*, int, long, cudaStream_t);
+int dwconv_ln(const void*, int, const float*, const float*, const float*, const float*, void*, int, int, int,
+              int, int, int, float, cudaStream_t);
+int dwconv_bias_act(const void*, int, const float*, const float*, void*, float*, int, int, int, int, int, int,
+                    int, int, int, int, int, cudaStream_t);
+int global_avg_pool(const void*, int, float*, int, int, int, cudaStream_t);
 
 }  // namespace tfimm
 
@@ -121,6 +126,23 @@ int tfimm_b200_assemble_tokens(const void* patches, int patch_dtype, const float
 
 int tfimm_b200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream) {
   return tfimm::cast_tensor(in, in_dtype, out, out_dtype, n, S(stream));
+}
+
+int tfimm_b200_dwconv_ln(const void* x, int in_dtype, const float* wgt, const float* bias, const float* gamma,
+                         const float* beta, void* out, int out_dtype, int B, int H, int W, int C, int ks,
+                         float eps, void* stream) {
+  return tfimm::dwconv_ln(x, in_dtype, wgt, bias, gamma, beta, out, out_dtype, B, H, W, C, ks, eps, S(stream));
+}
+
+int tfimm_b200_dwconv_bias_act(const void* x, int dtype, const float* wgt, const float* bias, void* out,
+                               float* pool_sum, int B, int H, int W, int C, int ks, int stride, int pad_t,
+                               int pad_l, int Ho, int Wo, int act, void* stream) {
+  return tfimm::dwconv_bias_act(x, dtype, wgt, bias, out, pool_sum, B, H, W, C, ks, stride, pad_t, pad_l, Ho, Wo,
+                                act, S(stream));
+}
+
+int tfimm_b200_global_avg_pool(const void* x, int dtype, float* out, int B, int HW, int C, void* stream) {
+  return tfimm::global_avg_pool(x, dtype, out, B, HW, C, S(stream));
 }
 
 }  // extern "C"

@@ -14,6 +14,8 @@
 // fp32 path (precision="fp32" parity mode): plain SIMT, one warp per query row.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace tfimm {
 namespace {
 
@@ -262,6 +264,8 @@ __global__ void attention_f32_kernel(const float* __restrict__ qkv, float* __res
 
 }  // namespace
 
+int attention_bf16_tc(const void* qkv, void* out, int B, int N, int H, float scale, cudaStream_t stream);
+
 int attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, float scale,
                    cudaStream_t stream) {
   TFIMM_CHECK_ARG(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
@@ -271,6 +275,13 @@ int attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, floa
   }
   TFIMM_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
                   "attention: pointers must be 16-byte aligned");
+  // Short sequences (ViT-B/16 @224: N = 197) run on tcgen05; longer ones on the resident-KV mma.sync
+  // kernel.  TFIMM_B200_ATTN=mma forces the latter (debugging aid).
+  static const bool force_mma = [] {
+    const char* e = getenv("TFIMM_B200_ATTN");
+    return e != nullptr && e[0] == 'm';
+  }();
+  if (N <= 256 && !force_mma) return attention_bf16_tc(qkv, out, B, N, H, scale, stream);
   auto q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   auto o = reinterpret_cast<__nv_bfloat16*>(out);
   if (N <= 128) return launch_vit_attention<4, 2>(q, o, B, N, H, scale, stream);

@@ -1,0 +1,202 @@
+// tcgen05 self-attention for short sequences (N <= 256 keys, head_dim 64): the ViT-B/16 case
+// (N = 197) of tfimm/architectures/vit.py:149-165.
+//
+// One CTA = one (image, head, 128-query tile); two CTAs are resident per SM so one CTA's loads /
+// softmax overlap the other's MMAs.
+//   TMA (3D maps over the packed qkv projection, zero-fill past the sequence end)
+//        Q tile [128 x 64], K [npad x 64], V [npad x 64] -> 128B-swizzled smem
+//   S = Q K^T        one tcgen05.mma chain (M=128, N=npad, K=64), fp32 scores in TMEM cols [0, npad)
+//   softmax          each thread owns one query row: tcgen05.ld, max, exp2, row sum in registers;
+//                    P (bf16) is written back over the consumed score columns (TMEM cols [0, npad/2))
+//   O = P V          tcgen05.mma with A = P from TMEM and B = V from smem as an MN-major operand
+//                    (V is [key][dh] in memory: no transpose pass), O in TMEM cols [128, 192)
+//   epilogue         O / rowsum -> bf16 -> swizzled smem slab -> TMA store (clipped at the sequence end)
+// The (B,H,N,N) score tensor the reference materialises never leaves the SM.
+#include "common.cuh"
+
+namespace tfimm {
+namespace {
+
+constexpr int kDH = 64;
+constexpr int kQRows = 128;
+constexpr int kMaxKeys = 256;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kOCol = 128;
+
+constexpr int kQBytes = kQRows * 128;          // 16 KB
+constexpr int kKVBytesMax = kMaxKeys * 128;    // 32 KB each
+constexpr int kSmemBytes = kQBytes + 2 * kKVBytesMax + 64 + 1024;
+
+__global__ void __launch_bounds__(128, 2)
+vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                        const __grid_constant__ CUtensorMap tmap_o, int N, int H, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sQ = smem_base;
+  const uint32_t sK = sQ + kQBytes;
+  const uint32_t sV = sK + kKVBytesMax;
+  const uint32_t bar_load = sV + kKVBytesMax;
+  const uint32_t bar_s = bar_load + 8;
+  const uint32_t bar_o = bar_load + 16;
+  const uint32_t tmem_ptr_smem = bar_load + 24;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kQRows, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * kDH;
+  const int npad = (N + 15) & ~15;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_kv);
+    prefetch_tmap(&tmap_o);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_load, (uint32_t)(kQBytes + 2 * npad * 128));
+    tma_load_3d(sQ, &tmap_q, bar_load, h * kDH, m0, b);
+    tma_load_3d(sK, &tmap_kv, bar_load, D + h * kDH, 0, b);
+    tma_load_3d(sV, &tmap_kv, bar_load, 2 * D + h * kDH, 0, b);
+    mbar_wait(bar_load, 0);
+    tcgen05_fence_after();
+    // S = Q K^T
+    const uint32_t idesc_s = umma_idesc_bf16_f32(kQRows, npad);
+    const uint64_t dq = umma_desc_k_sw128(sQ), dk = umma_desc_k_sw128(sK);
+#pragma unroll
+    for (int k = 0; k < kDH / 16; ++k)
+      umma_bf16_ss(tmem_base, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+    umma_commit(bar_s);
+  }
+  mbar_wait(bar_s, 0);
+  tcgen05_fence_after();
+
+  // ---- softmax: thread (warp, lane) owns query row m0 + 32*warp + lane (TMEM lane 32*warp + lane) ----
+  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const bool warp_has_rows = (m0 + warp * 32) < N;
+  float row_sum = 1.f;
+  if (warp_has_rows) {
+    const int nchunks = npad >> 4;
+    float mx = -INFINITY;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 16), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c * 16 + j < N) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+    const float moff = mx * scale_log2;
+    row_sum = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 16), r);
+      tmem_ld_wait();
+      float pv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float e = ex2_approx(fmaf(__uint_as_float(r[j]), scale_log2, -moff));
+        pv[j] = (c * 16 + j < N) ? e : 0.f;
+        row_sum += pv[j];
+      }
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(pv[2 * j], pv[2 * j + 1]);
+      tmem_st_32x32b_x8(t_row + (uint32_t)(c * 8), pk);
+    }
+    tmem_st_wait();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+
+  if (threadIdx.x == 0) {
+    // O = P V : A = P (TMEM, 8 packed columns per 16 keys), B = V (smem, MN-major, 16 keys = 2048 B)
+    const uint32_t idesc_o = umma_idesc_bf16_f32(kQRows, kDH, /*b_mn_major=*/true);
+    const int ksteps = npad >> 4;
+    for (int j = 0; j < ksteps; ++j) {
+      const uint64_t dv = umma_desc_mn_sw128(sV + (uint32_t)(j * 2048), (uint32_t)(npad * 128));
+      umma_bf16_ts(tmem_base + kOCol, tmem_base + (uint32_t)(j * 8), dv, idesc_o, (uint32_t)(j != 0));
+    }
+    umma_commit(bar_o);
+  }
+  mbar_wait(bar_o, 0);
+  tcgen05_fence_after();
+
+  if (warp_has_rows) {
+    const float inv = 1.0f / row_sum;
+    uint8_t* my_row = smem_gen + (size_t)warp * 4096 + lane * 128;  // Q region is dead: reuse as store slab
+    const int sw = lane & 7;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(t_row + kOCol + (uint32_t)(c * 16), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(r[8 * q + 0]) * inv, __uint_as_float(r[8 * q + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv);
+        *reinterpret_cast<uint4*>(my_row + (((2 * c + q) ^ sw) << 4)) = u;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(&tmap_o, sQ + (uint32_t)warp * 4096u, h * kDH, m0 + warp * 32, b);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace
+
+int attention_bf16_tc(const void* qkv, void* out, int B, int N, int H, float scale, cudaStream_t stream) {
+  const int D = H * kDH;
+  const int npad = (N + 15) & ~15;
+  CUtensorMap tq, tkv, to;
+  {
+    const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)N, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)N * 3 * D * 2};
+    const uint32_t box_q[3] = {kDH, kQRows, 1};
+    const uint32_t box_kv[3] = {kDH, (uint32_t)npad, 1};
+    int st;
+    if ((st = make_tmap(&tq, qkv, kBF16, 3, dims, strides, box_q, "attention q")) != kOk) return st;
+    if ((st = make_tmap(&tkv, qkv, kBF16, 3, dims, strides, box_kv, "attention kv")) != kOk) return st;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)N, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)N * D * 2};
+    const uint32_t box[3] = {kDH, 32, 1};
+    int st;
+    if ((st = make_tmap(&to, out, kBF16, 3, dims, strides, box, "attention out")) != kOk) return st;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    TFIMM_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((N + kQRows - 1) / kQRows, H, B);
+  vit_attention_tc_kernel<<<grid, 128, kSmemBytes, stream>>>(tq, tkv, to, N, H, scale * 1.4426950408889634f);
+  TFIMM_LAUNCH_OK("vit_attention_tc_kernel");
+  return kOk;
+}
+
+}  // namespace tfimm

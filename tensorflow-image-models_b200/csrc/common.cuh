@@ -63,26 +63,44 @@ enum Act : int {
 
 int sm_count();
 
+// tmap.cu: TMA descriptors (SWIZZLE_128B, zero OOB fill)
+int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, const char* what);
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols, const char* what);
+
 // ----------------------------------------------------------------------------
 // Small device math
 // ----------------------------------------------------------------------------
 #if defined(__CUDACC__)
 
-// erf(x) with |abs err| < 1.5e-7 (Abramowitz & Stegun 7.1.26).  Cheap enough
-// to live in a GEMM epilogue: one MUFU.RCP, one MUFU.EX2, ~10 FMA-pipe ops.
-__device__ __forceinline__ float fast_erff(float x) {
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// GELU (exact erf form) for GEMM epilogues: x * Phi(x) with
+//   erfc(z) ~= t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),  t = 1 / (1 + p z),  z = |x| / sqrt(2)
+// (Abramowitz & Stegun 7.1.26, |abs err| < 1.5e-7 on erfc).  Written on the erfc side so there is no
+// cancellation for negative x.  Two MUFU ops (rcp, ex2) + ~14 FMA-pipe ops per element.
+__device__ __forceinline__ float gelu_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678f, ax, 1.0f));
   float p = 1.061405429f;
   p = fmaf(p, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  // exp(-x^2) = exp2(-x^2 * log2 e)
-  const float e = exp2f(-ax * ax * 1.4426950408889634f);
-  const float r = fmaf(-p, e, 1.0f);
-  return copysignf(r, x);
+  // exp(-x^2 / 2) = exp2(-x^2 * log2(e) / 2)
+  const float e = ex2_approx(ax * ax * -0.72134752044448170368f);
+  const float h = 0.5f * ax * (p * t * e);  // |x| * Phi(-|x|)
+  return x > 0.f ? x - h : -h;
 }
 
 template <bool kPrecise>
@@ -90,7 +108,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
   if constexpr (kPrecise) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
   } else {
-    return 0.5f * x * (1.0f + fast_erff(x * 0.70710678118654752440f));
+    return gelu_fast(x);
   }
 }
 
@@ -99,7 +117,7 @@ __device__ __forceinline__ float sigmoidf_(float x) {
   if constexpr (kPrecise) {
     return 1.0f / (1.0f + expf(-x));
   } else {
-    return __frcp_rn(1.0f + exp2f(-x * 1.4426950408889634f));
+    return rcp_approx(1.0f + ex2_approx(-x * 1.4426950408889634f));
   }
 }
 
@@ -113,6 +131,39 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case kActTanh: return tanhf(v);
     case kActSigmoid: return sigmoidf_<kPrecise>(v);
     default: return v;
+  }
+}
+
+// Activation over a register array with the switch hoisted out of the element loop.
+template <bool kPrecise, int N>
+__device__ __forceinline__ void apply_act_array(float (&v)[N], int act) {
+  switch (act) {
+    case kActGelu:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = gelu_erf<kPrecise>(v[j]);
+      break;
+    case kActSwish:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = v[j] * sigmoidf_<kPrecise>(v[j]);
+      break;
+    case kActRelu:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.0f);
+      break;
+    case kActRelu6:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = fminf(fmaxf(v[j], 0.0f), 6.0f);
+      break;
+    case kActTanh:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = tanhf(v[j]);
+      break;
+    case kActSigmoid:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = sigmoidf_<kPrecise>(v[j]);
+      break;
+    default:
+      break;
   }
 }
 
@@ -254,6 +305,21 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem
       ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src_smem), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3D variants (innermost coordinate first).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -316,6 +382,39 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+// TMEM -> registers: this warp's 32 lanes x 16 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x 8 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: A rows live in TMEM lanes, K packed two bf16 per 32-bit column.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -336,12 +435,27 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Same for an MN-major operand (e.g. V[key][dh] used as B[N = dh][K = key]): rows of 64 bf16 along MN
+// (one 128-byte swizzle span), consecutive K indices 128 bytes apart, 8-row swizzle groups 1024 bytes
+// apart (SBO); LBO = distance between 64-element MN blocks (unused when the MN extent is 64).
+// Canonical layout: cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B (both K-major), fp32 D.
 // Field layout: cute/arch/mma_sm100_desc.hpp (InstrDescriptor).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int m, int n) {
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int m, int n, bool b_mn_major = false) {
   return (1u << 4)                    // c_format = F32
          | (1u << 7)                  // a_format = BF16
          | (1u << 10)                 // b_format = BF16
+         | ((b_mn_major ? 1u : 0u) << 16)  // b_major: 0 = K-major, 1 = MN-major
          | ((uint32_t)(n >> 3) << 17) // n_dim
          | ((uint32_t)(m >> 4) << 24);  // m_dim
 }

@@ -1,0 +1,340 @@
+// Depthwise convolutions and pooling (CUDA-core / HBM-bound part of the conv families).
+//
+//   dwconv_ln        ZeroPad(k/2) -> DepthwiseConv2D(k x k, stride 1, bias) -> LayerNorm over C,
+//                    the first half of ConvNeXtBlock.call (tfimm/architectures/convnext.py:219-228,
+//                    layers built at :189-198).  One warp owns a strip of TW output pixels of one row
+//                    and ALL channels (LN needs every channel of a pixel); channel groups of 128 are
+//                    processed with a sliding register window along x, the k*k*C fp32 taps are read
+//                    through L1, and the pre-norm values are parked in shared memory for the
+//                    two-pass fp32 LayerNorm.
+//   dwconv_bias_act  DepthwiseConv2D(k, stride, explicit 4-sided padding) + folded-BN bias + act,
+//                    with optional fused squeeze (per-image channel sums for SqueezeExcite):
+//                    tfimm/architectures/efficientnet_blocks.py:312-323,393-404,241-242.
+//   global_avg_pool  GlobalAveragePooling2D / reduce_mean over H,W (convnext.py:433,
+//                    efficientnet.py:256, swin.py:456, layers/classifier.py:34).
+#include "common.cuh"
+
+namespace tfimm {
+namespace {
+
+// ----------------------------------------------------------------------------------------------
+// dwconv (stride 1, "same" symmetric zero pad) + bias + LayerNorm
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4f(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4f(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4f(__nv_bfloat16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename InT, typename OutT, int KS, int TW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+dwconv_ln_kernel(const InT* __restrict__ x, const float* __restrict__ wgt /*[KS*KS][C]*/,
+                 const float* __restrict__ bias, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, OutT* __restrict__ out, int B, int H, int W, int C,
+                 float eps) {
+  constexpr int PAD = KS / 2;
+  extern __shared__ __align__(16) float sh[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* stash = sh + (size_t)warp * TW * C;  // [TW][C] pre-norm values of this warp's strip
+  const int segs = (W + TW - 1) / TW;
+  // unit order (b, seg, y) with y fastest: the WARPS warps of a CTA take adjacent rows (L1 reuse)
+  const long unit = (long)blockIdx.x * WARPS + warp;
+  const long units = (long)B * segs * H;
+  if (unit >= units) return;
+  const int y = (int)(unit % H);
+  const long t = unit / H;
+  const int seg = (int)(t % segs);
+  const int b = (int)(t / segs);
+  const int x0 = seg * TW;
+  const int groups = C >> 7;  // 128 channels (4 per lane) per group; C % 128 handled by tail group
+  const int tail = C & 127;
+  float psum[TW];
+#pragma unroll
+  for (int i = 0; i < TW; ++i) psum[i] = 0.f;
+
+  const int ngroups = groups + (tail ? 1 : 0);
+  for (int gidx = 0; gidx < ngroups; ++gidx) {
+    const int c = gidx * 128 + lane * 4;
+    const bool cvalid = c < C;  // C % 4 == 0 is required, so a lane is fully in or out
+    float4 acc[TW];
+    const float4 bv = cvalid ? ld4f(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < TW; ++i) acc[i] = bv;
+    if (cvalid) {
+#pragma unroll 1
+      for (int ky = 0; ky < KS; ++ky) {
+        const int iy = y + ky - PAD;
+        if (iy < 0 || iy >= H) continue;
+        float4 wv[KS];
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) wv[kx] = ld4f(wgt + (size_t)(ky * KS + kx) * C + c);
+        const InT* row = x + (((long)b * H + iy) * W) * C + c;
+#pragma unroll
+        for (int ix = 0; ix < TW + KS - 1; ++ix) {
+          const int gx = x0 + ix - PAD;
+          if (gx < 0 || gx >= W) continue;
+          const float4 v = ld4f(row + (long)gx * C);
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) {
+            const int ox = ix - kx;  // output pixel this (input, tap) pair contributes to
+            if (ox >= 0 && ox < TW) {
+              acc[ox].x = fmaf(v.x, wv[kx].x, acc[ox].x);
+              acc[ox].y = fmaf(v.y, wv[kx].y, acc[ox].y);
+              acc[ox].z = fmaf(v.z, wv[kx].z, acc[ox].z);
+              acc[ox].w = fmaf(v.w, wv[kx].w, acc[ox].w);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TW; ++i) {
+        *reinterpret_cast<float4*>(stash + (size_t)i * C + c) = acc[i];
+        psum[i] += acc[i].x + acc[i].y + acc[i].z + acc[i].w;
+      }
+    }
+  }
+  __syncwarp();
+  // two-pass LayerNorm per pixel over the stashed values
+#pragma unroll 1
+  for (int i = 0; i < TW; ++i) {
+    if (x0 + i >= W) break;
+    const float mean = warp_sum(psum[i]) / (float)C;
+    float sq = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(stash + (size_t)i * C + c);
+      const float a = v.x - mean, bq = v.y - mean, cq = v.z - mean, d = v.w - mean;
+      sq += a * a + bq * bq + cq * cq + d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+    OutT* orow = out + (((long)b * H + y) * W + (x0 + i)) * C;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(stash + (size_t)i * C + c);
+      const float4 g = ld4f(gamma + c), be = ld4f(beta + c);
+      float4 o;
+      o.x = (v.x - mean) * rstd * g.x + be.x;
+      o.y = (v.y - mean) * rstd * g.y + be.y;
+      o.z = (v.z - mean) * rstd * g.z + be.z;
+      o.w = (v.w - mean) * rstd * g.w + be.w;
+      st4f(orow + c, o);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// generic depthwise conv + bias + activation (+ fused squeeze)
+// ----------------------------------------------------------------------------------------------
+// One thread: 4 channels x TW output pixels of one output row.  Threads of a warp cover 128
+// consecutive channels (coalesced 8-byte/16-byte accesses); warps tile (channel group, x strip, y, b).
+template <typename T, int KS, int STRIDE, int TW>
+__global__ void __launch_bounds__(128)
+dwconv_act_kernel(const T* __restrict__ x, const float* __restrict__ wgt /*[KS*KS][C]*/,
+                  const float* __restrict__ bias, T* __restrict__ out, float* __restrict__ pool_sum,
+                  int B, int H, int W, int C, int Ho, int Wo, int pad_t, int pad_l, int act) {
+  const int cgroups = (C + 127) >> 7;
+  const int segs = (Wo + TW - 1) / TW;
+  const long unit = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const long units = (long)B * Ho * segs * cgroups;
+  if (unit >= units) return;
+  const int lane = threadIdx.x & 31;
+  const int cg = (int)(unit % cgroups);
+  long t = unit / cgroups;
+  const int oy = (int)(t % Ho);
+  t /= Ho;
+  const int seg = (int)(t % segs);
+  const int b = (int)(t / segs);
+  const int c = cg * 128 + lane * 4;
+  if (c >= C) return;
+  const int ox0 = seg * TW;
+  constexpr int IW = (TW - 1) * STRIDE + KS;  // input columns feeding the strip
+  float4 acc[TW];
+  const float4 bv = bias != nullptr ? ld4f(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < TW; ++i) acc[i] = bv;
+#pragma unroll 1
+  for (int ky = 0; ky < KS; ++ky) {
+    const int iy = oy * STRIDE + ky - pad_t;
+    if (iy < 0 || iy >= H) continue;
+    float4 wv[KS];
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx) wv[kx] = ld4f(wgt + (size_t)(ky * KS + kx) * C + c);
+    const T* row = x + (((long)b * H + iy) * W) * C + c;
+#pragma unroll
+    for (int ix = 0; ix < IW; ++ix) {
+      const int gx = ox0 * STRIDE + ix - pad_l;
+      if (gx < 0 || gx >= W) continue;
+      const float4 v = ld4f(row + (long)gx * C);
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        // ix = ox*STRIDE + kx
+        if ((ix - kx) >= 0 && (ix - kx) % STRIDE == 0 && (ix - kx) / STRIDE < TW) {
+          const int ox = (ix - kx) / STRIDE;
+          acc[ox].x = fmaf(v.x, wv[kx].x, acc[ox].x);
+          acc[ox].y = fmaf(v.y, wv[kx].y, acc[ox].y);
+          acc[ox].z = fmaf(v.z, wv[kx].z, acc[ox].z);
+          acc[ox].w = fmaf(v.w, wv[kx].w, acc[ox].w);
+        }
+      }
+    }
+  }
+  float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < TW; ++i) {
+    if (ox0 + i < Wo) {
+      float4 o;
+      o.x = apply_act<true>(acc[i].x, act);
+      o.y = apply_act<true>(acc[i].y, act);
+      o.z = apply_act<true>(acc[i].z, act);
+      o.w = apply_act<true>(acc[i].w, act);
+      // round first so the pooled statistics see exactly what the next layer reads
+      T* dst = out + (((long)b * Ho + oy) * Wo + ox0 + i) * C + c;
+      st4f(dst, o);
+      if (pool_sum != nullptr) {
+        if constexpr (sizeof(T) == 2) {
+          const float2 r0 = unpack_bf16x2(pack_bf16x2(o.x, o.y)), r1 = unpack_bf16x2(pack_bf16x2(o.z, o.w));
+          ps.x += r0.x; ps.y += r0.y; ps.z += r1.x; ps.w += r1.y;
+        } else {
+          ps.x += o.x; ps.y += o.y; ps.z += o.z; ps.w += o.w;
+        }
+      }
+    }
+  }
+  if (pool_sum != nullptr) {
+    float* p = pool_sum + (long)b * C + c;
+    atomicAdd(p + 0, ps.x);
+    atomicAdd(p + 1, ps.y);
+    atomicAdd(p + 2, ps.z);
+    atomicAdd(p + 3, ps.w);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// global average pool: (B, HW, C) -> (B, C) fp32
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void global_avg_pool_kernel(const T* __restrict__ x, float* __restrict__ out, int HW, int C) {
+  // grid: (ceil(C/128), B); block 128 threads = 4 pixel-phases x 32 lanes of 4 channels
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  __shared__ float4 red[4][32];
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    const T* base = x + (long)b * HW * C + c;
+    for (int p = ph; p < HW; p += 4) {
+      const float4 v = ld4f(base + (long)p * C);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  red[ph][lane] = s;
+  __syncthreads();
+  if (ph == 0 && c < C) {
+    float4 a = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+      a.x += red[i][lane].x; a.y += red[i][lane].y; a.z += red[i][lane].z; a.w += red[i][lane].w;
+    }
+    const float inv = 1.0f / (float)HW;
+    *reinterpret_cast<float4*>(out + (long)b * C + c) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  }
+}
+
+}  // namespace
+
+int dwconv_ln(const void* x, int in_dtype, const float* wgt, const float* bias, const float* gamma,
+              const float* beta, void* out, int out_dtype, int B, int H, int W, int C, int ks, float eps,
+              cudaStream_t stream) {
+  TFIMM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "dwconv_ln: need C%%4==0 (C=%d)", C);
+  TFIMM_CHECK_ARG(ks == 7, "dwconv_ln: only kernel size 7 is instantiated (got %d)", ks);
+  constexpr int TW = 7;
+  // warps per CTA limited by the [TW][C] fp32 stash per warp
+  const size_t per_warp = (size_t)TW * C * sizeof(float);
+  int warps = 4;
+  while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+  if (per_warp * warps > 227 * 1024) {
+    set_last_error("dwconv_ln: C=%d too large for the shared-memory stash", C);
+    return kUnsupported;
+  }
+  const long units = (long)B * ((W + TW - 1) / TW) * H;
+  const size_t smem = per_warp * warps;
+#define TFIMM_DWLN(IN, OUT, WARPS)                                                                      \
+  do {                                                                                                  \
+    auto k = dwconv_ln_kernel<IN, OUT, 7, TW, WARPS>;                                                   \
+    if (smem > 48 * 1024)                                                                               \
+      TFIMM_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    k<<<(unsigned)((units + WARPS - 1) / WARPS), WARPS * 32, smem, stream>>>(                           \
+        reinterpret_cast<const IN*>(x), wgt, bias, gamma, beta, reinterpret_cast<OUT*>(out), B, H, W, C, eps); \
+  } while (0)
+#define TFIMM_DWLN_W(IN, OUT)                  \
+  do {                                         \
+    if (warps == 4) TFIMM_DWLN(IN, OUT, 4);    \
+    else if (warps == 2) TFIMM_DWLN(IN, OUT, 2); \
+    else TFIMM_DWLN(IN, OUT, 1);               \
+  } while (0)
+  if (in_dtype == kF32 && out_dtype == kBF16) TFIMM_DWLN_W(float, __nv_bfloat16);
+  else if (in_dtype == kBF16 && out_dtype == kBF16) TFIMM_DWLN_W(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == kF32 && out_dtype == kF32) TFIMM_DWLN_W(float, float);
+  else {
+    set_last_error("dwconv_ln: unsupported dtype combination in=%d out=%d", in_dtype, out_dtype);
+    return kInvalidArgument;
+  }
+#undef TFIMM_DWLN_W
+#undef TFIMM_DWLN
+  TFIMM_LAUNCH_OK("dwconv_ln_kernel");
+  return kOk;
+}
+
+int dwconv_bias_act(const void* x, int dtype, const float* wgt, const float* bias, void* out, float* pool_sum,
+                    int B, int H, int W, int C, int ks, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                    int act, cudaStream_t stream) {
+  TFIMM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "dwconv: need C%%4==0 (C=%d)", C);
+  TFIMM_CHECK_ARG((ks == 3 || ks == 5 || ks == 7) && (stride == 1 || stride == 2),
+                  "dwconv: kernel size 3/5/7 and stride 1/2 are instantiated (got k=%d s=%d)", ks, stride);
+  TFIMM_CHECK_ARG(dtype == kBF16 || dtype == kF32, "dwconv: dtype must be bf16 or f32");
+  constexpr int TW = 4;
+  const long units = (long)B * Ho * ((Wo + TW - 1) / TW) * ((C + 127) / 128);
+  const unsigned grid = (unsigned)((units + 3) / 4);
+#define TFIMM_DW(T, KS, ST)                                                                              \
+  dwconv_act_kernel<T, KS, ST, TW><<<grid, 128, 0, stream>>>(reinterpret_cast<const T*>(x), wgt, bias,    \
+                                                            reinterpret_cast<T*>(out), pool_sum, B, H, W, \
+                                                            C, Ho, Wo, pad_t, pad_l, act)
+#define TFIMM_DW_T(T)                             \
+  do {                                            \
+    if (ks == 3 && stride == 1) TFIMM_DW(T, 3, 1); \
+    else if (ks == 3) TFIMM_DW(T, 3, 2);          \
+    else if (ks == 5 && stride == 1) TFIMM_DW(T, 5, 1); \
+    else if (ks == 5) TFIMM_DW(T, 5, 2);          \
+    else if (stride == 1) TFIMM_DW(T, 7, 1);      \
+    else TFIMM_DW(T, 7, 2);                       \
+  } while (0)
+  if (dtype == kBF16) TFIMM_DW_T(__nv_bfloat16);
+  else TFIMM_DW_T(float);
+#undef TFIMM_DW_T
+#undef TFIMM_DW
+  TFIMM_LAUNCH_OK("dwconv_act_kernel");
+  return kOk;
+}
+
+int global_avg_pool(const void* x, int dtype, float* out, int B, int HW, int C, cudaStream_t stream) {
+  TFIMM_CHECK_ARG(B > 0 && HW > 0 && C > 0 && C % 4 == 0, "global_avg_pool: need C%%4==0");
+  dim3 grid((C + 127) / 128, B);
+  if (dtype == kBF16)
+    global_avg_pool_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, HW, C);
+  else if (dtype == kF32)
+    global_avg_pool_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const float*>(x), out, HW, C);
+  else {
+    set_last_error("global_avg_pool: dtype must be bf16 or f32");
+    return kInvalidArgument;
+  }
+  TFIMM_LAUNCH_OK("global_avg_pool_kernel");
+  return kOk;
+}
+
+}  // namespace tfimm

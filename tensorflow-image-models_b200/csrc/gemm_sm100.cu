@@ -19,8 +19,6 @@
 //               slab and may alias the output (in-place residual stream).
 #include "common.cuh"
 
-#include <cudaTypedefs.h>
-#include <mutex>
 
 namespace tfimm {
 namespace {
@@ -225,10 +223,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
               if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
           }
         }
-        if (p.act != kActNone) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = apply_act<false>(v[j], p.act);
-        }
+        if (p.act != kActNone) apply_act_array<false>(v, p.act);
         if (p.gamma != nullptr) {
           if (full_chunk) {
 #pragma unroll
@@ -302,52 +297,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 // ------------------------------ host side -----------------------------------
-PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
-            cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-    }
-  });
-  return fn;
-}
-
-// 2D row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols].
-int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint64_t cols,
-                 uint64_t ld, uint32_t box_rows, uint32_t box_cols, const char* what) {
-  auto encode = get_encode_fn();
-  if (encode == nullptr) {
-    set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
-    return kCudaError;
-  }
-  const uint64_t esize = dtype == kBF16 ? 2 : 4;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || ((ld * esize) & 15u) != 0) {
-    set_last_error("gemm: %s must be 16-byte aligned with a 16-byte multiple row pitch (ptr=%p ld=%llu)",
-                   what, ptr, (unsigned long long)ld);
-    return kInvalidArgument;
-  }
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * esize};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode(map, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                      2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)",
-                   what, (int)r, (unsigned long long)rows, (unsigned long long)cols,
-                   (unsigned long long)ld, box_rows, box_cols);
-    return kCudaError;
-  }
-  return kOk;
-}
-
 template <int BLOCK_N, typename OutT>
 int launch_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
                 const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act,

@@ -1,0 +1,2 @@
+from .convnext import *  # noqa: F401,F403
+from .vit import *  # noqa: F401,F403

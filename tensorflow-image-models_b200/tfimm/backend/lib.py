@@ -37,6 +37,9 @@ SIGNATURES = {
     "tfimm_b200_patchify": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
     "tfimm_b200_assemble_tokens": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "tfimm_b200_cast": [_P, _I, _P, _I, _L, _P],
+    "tfimm_b200_dwconv_ln": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "tfimm_b200_dwconv_bias_act": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "tfimm_b200_global_avg_pool": [_P, _I, _P, _I, _I, _I, _P],
 }
 _SPECIAL = {
     "tfimm_b200_version": ([], _c.c_char_p),

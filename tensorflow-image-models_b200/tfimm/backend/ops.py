@@ -39,11 +39,28 @@ def _cuda(*tensors):
             )
 
 
-def _call(name, *args):
+# When set to a list, every launch is bracketed by CUDA events on the launching stream and
+# (family, start, end, algorithmic flops, algorithmic bytes) is appended (bench.py roofline pass).
+trace = None
+
+
+def _call(name, *args, flops=0.0, nbytes=0.0):
     global launch_count
     fn = getattr(_lib.load(), name)
-    _lib.check(fn(*args), name)
+    if trace is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(fn(*args), name)
+        e1.record()
+        trace.append((name.replace("tfimm_b200_", ""), e0, e1, float(flops), float(nbytes)))
+    else:
+        _lib.check(fn(*args), name)
     launch_count += 1
+
+
+def _nbytes(*tensors):
+    return float(sum(t.numel() * t.element_size() for t in tensors if t is not None))
 
 
 def act_code(act) -> int:
@@ -73,12 +90,13 @@ def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dty
         assert w.dtype == torch.bfloat16
         _call("tfimm_b200_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
               _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
-              _code(out), block_n, _stream())
+              _code(out), block_n, _stream(), flops=2.0 * M * N * K,
+              nbytes=_nbytes(a, w, out, residual))
     else:
         assert a.dtype == torch.float32 and w.dtype == torch.float32 and out.dtype == torch.float32
         _call("tfimm_b200_gemm_f32", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
               _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
-              _stream())
+              _stream(), flops=2.0 * M * N * K, nbytes=_nbytes(a, w, out, residual))
     return out
 
 
@@ -90,7 +108,8 @@ def layernorm(x, gamma, beta, eps, out_dtype, out=None):
     if out is None:
         out = torch.empty((rows, C), device=x.device, dtype=out_dtype)
     _call("tfimm_b200_layernorm", x.data_ptr(), _code(x), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
-          out.data_ptr(), _code(out), out.stride(0), rows, C, float(eps), _stream())
+          out.data_ptr(), _code(out), out.stride(0), rows, C, float(eps), _stream(),
+          nbytes=rows * C * (x.element_size() + out.element_size()))
     return out
 
 
@@ -101,7 +120,7 @@ def layernorm_patch2x2(x, gamma, beta, eps, out_dtype):
     assert x.is_contiguous()
     out = torch.empty((B * (H // 2) * (W // 2), 4 * C), device=x.device, dtype=out_dtype)
     _call("tfimm_b200_layernorm_patch2x2", x.data_ptr(), _code(x), gamma.data_ptr(), beta.data_ptr(),
-          out.data_ptr(), _code(out), B, H, W, C, float(eps), _stream())
+          out.data_ptr(), _code(out), B, H, W, C, float(eps), _stream(), nbytes=_nbytes(x, out))
     return out
 
 
@@ -112,7 +131,7 @@ def patch_merge_ln(x, gamma, beta, eps, out_dtype):
     assert x.is_contiguous()
     out = torch.empty((B * (H // 2) * (W // 2), 4 * C), device=x.device, dtype=out_dtype)
     _call("tfimm_b200_patch_merge_ln", x.data_ptr(), _code(x), gamma.data_ptr(), beta.data_ptr(),
-          out.data_ptr(), _code(out), B, H, W, C, float(eps), _stream())
+          out.data_ptr(), _code(out), B, H, W, C, float(eps), _stream(), nbytes=_nbytes(x, out))
     return out
 
 
@@ -122,11 +141,13 @@ def attention(qkv, B, N, H, dh, scale, bias=None, mask=None, probs=None):
     assert qkv.shape == (B * N, 3 * H * dh) and qkv.is_contiguous()
     out = torch.empty((B * N, H * dh), device=qkv.device, dtype=qkv.dtype)
     if qkv.dtype == torch.bfloat16 and bias is None and mask is None and probs is None:
-        _call("tfimm_b200_attention_bf16", qkv.data_ptr(), out.data_ptr(), B, N, H, dh, float(scale), _stream())
+        _call("tfimm_b200_attention_bf16", qkv.data_ptr(), out.data_ptr(), B, N, H, dh, float(scale), _stream(),
+              flops=4.0 * B * H * N * N * dh, nbytes=_nbytes(qkv, out))
     elif qkv.dtype == torch.float32:
         nmask = mask.shape[0] if mask is not None else 1
         _call("tfimm_b200_attention_f32", qkv.data_ptr(), out.data_ptr(), _ptr(bias), _ptr(mask), nmask, B, N,
-              H, dh, float(scale), _ptr(probs), _stream())
+              H, dh, float(scale), _ptr(probs), _stream(), flops=4.0 * B * H * N * N * dh,
+              nbytes=_nbytes(qkv, out, probs))
     else:
         raise _lib.KernelLibraryError("attention: unsupported dtype / option combination")
     return out
@@ -141,7 +162,7 @@ def patchify(img, p, out_dtype, mean=None, inv_std=None, scale=1.0):
     Kpad = (K + 7) // 8 * 8
     out = torch.empty((B * (H // p) * (W // p), Kpad), device=img.device, dtype=out_dtype)
     _call("tfimm_b200_patchify", img.data_ptr(), _code(img), out.data_ptr(), _code(out), B, H, W, C, p, Kpad,
-          float(scale), _ptr(mean), _ptr(inv_std), _stream())
+          float(scale), _ptr(mean), _ptr(inv_std), _stream(), nbytes=_nbytes(img, out))
     return out
 
 
@@ -151,7 +172,7 @@ def assemble_tokens(patches, cls, dist, pos, B, P, out_dtype):
     ntok = 2 if dist is not None else 1
     out = torch.empty((B * (P + ntok), D), device=patches.device, dtype=out_dtype)
     _call("tfimm_b200_assemble_tokens", patches.data_ptr(), _code(patches), cls.data_ptr(), _ptr(dist),
-          pos.data_ptr(), out.data_ptr(), _code(out), B, P, ntok, D, _stream())
+          pos.data_ptr(), out.data_ptr(), _code(out), B, P, ntok, D, _stream(), nbytes=_nbytes(patches, out))
     return out
 
 
@@ -161,5 +182,64 @@ def cast(x, dtype):
         return x
     x = x.contiguous()
     out = torch.empty(x.shape, device=x.device, dtype=dtype)
-    _call("tfimm_b200_cast", x.data_ptr(), _code(x), out.data_ptr(), _code(out), x.numel(), _stream())
+    _call("tfimm_b200_cast", x.data_ptr(), _code(x), out.data_ptr(), _code(out), x.numel(), _stream(),
+          nbytes=_nbytes(x, out))
+    return out
+
+
+def dwconv_ln(x, wgt, bias, gamma, beta, eps, out_dtype):
+    """ConvNeXt block head: depthwise 7x7 (pad 3, bias) + LayerNorm.  x: (B,H,W,C) -> (B*H*W, C)."""
+    _cuda(x, wgt, bias, gamma, beta)
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    ks = int(round((wgt.shape[0]) ** 0.5))
+    out = torch.empty((B * H * W, C), device=x.device, dtype=out_dtype)
+    _call("tfimm_b200_dwconv_ln", x.data_ptr(), _code(x), wgt.data_ptr(), bias.data_ptr(), gamma.data_ptr(),
+          beta.data_ptr(), out.data_ptr(), _code(out), B, H, W, C, ks, float(eps), _stream(),
+          flops=2.0 * B * H * W * C * ks * ks, nbytes=_nbytes(x, out))
+    return out
+
+
+def same_pad(size, k, s):
+    """TF "same": returns (out_size, pad_before)."""
+    out = -(-size // s)
+    total = max((out - 1) * s + k - size, 0)
+    return out, total // 2
+
+
+def dwconv_bias_act(x, wgt, bias, ks, stride, padding, act=None, pool_sum=None):
+    """Depthwise conv + bias + act.  padding: "same" (TF, asymmetric) | "symmetric" | "valid".
+    x: (B,H,W,C) -> (B,Ho,Wo,C); pool_sum: optional (B,C) fp32 zero-initialised accumulator."""
+    _cuda(x, wgt, bias, pool_sum)
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    if padding == "same":
+        Ho, pt = same_pad(H, ks, stride)
+        Wo, pl = same_pad(W, ks, stride)
+    elif padding == "symmetric":
+        pt = pl = ((stride - 1) + (ks - 1)) // 2
+        Ho = (H + 2 * pt - ks) // stride + 1
+        Wo = (W + 2 * pl - ks) // stride + 1
+    elif padding == "valid":
+        pt = pl = 0
+        Ho = (H - ks) // stride + 1
+        Wo = (W - ks) // stride + 1
+    else:
+        raise ValueError(f"Unknown padding {padding}")
+    out = torch.empty((B, Ho, Wo, C), device=x.device, dtype=x.dtype)
+    _call("tfimm_b200_dwconv_bias_act", x.data_ptr(), _code(x), wgt.data_ptr(), _ptr(bias), out.data_ptr(),
+          _ptr(pool_sum), B, H, W, C, ks, stride, pt, pl, Ho, Wo, act_code(act), _stream(),
+          flops=2.0 * B * Ho * Wo * C * ks * ks, nbytes=_nbytes(x, out))
+    return out
+
+
+def global_avg_pool(x):
+    """(B, HW, C) or (B, H, W, C) -> (B, C) fp32 mean over the spatial axes."""
+    _cuda(x)
+    assert x.is_contiguous()
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    out = torch.empty((B, C), device=x.device, dtype=torch.float32)
+    _call("tfimm_b200_global_avg_pool", x.data_ptr(), _code(x), out.data_ptr(), B, HW, C, _stream(),
+          nbytes=_nbytes(x, out))
     return out

@@ -261,3 +261,67 @@ def test_assemble_tokens():
         toks = [cls[None, None].expand(B, 1, D)] + ([d[None, None].expand(B, 1, D)] if d is not None else [])
         ref = torch.cat(toks + [patches.float().view(B, P, D)], dim=1) + pos[None]
         assert (out.view(B, P + ntok, D) - ref).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("C,H,W", [(128, 56, 56), (256, 28, 28), (512, 14, 14), (1024, 7, 7), (96, 9, 13), (192, 5, 3)])
+@pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.bfloat16), (torch.float32, torch.float32),
+                                                (torch.bfloat16, torch.bfloat16)])
+def test_dwconv7x7_ln(C, H, W, in_dtype, out_dtype):
+    ops = _ops()
+    B = 2
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(in_dtype)
+    wgt = torch.randn(49, C, device="cuda", generator=g) / 7
+    bias = torch.randn(C, device="cuda", generator=g)
+    gamma = torch.randn(C, device="cuda", generator=g)
+    beta = torch.randn(C, device="cuda", generator=g)
+    out = ops.dwconv_ln(x, wgt, bias, gamma, beta, 1e-6, out_dtype)
+    torch.cuda.synchronize()
+    wt = wgt.view(7, 7, C).permute(2, 0, 1)[:, None]  # (C,1,7,7)
+    y = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=3, groups=C).permute(0, 2, 3, 1)
+    ref = torch.nn.functional.layer_norm(y, (C,), gamma, beta, 1e-6).reshape(-1, C)
+    tol = 2e-4 if out_dtype == torch.float32 else 2.0 ** -8 * ref.abs().max().item() + 1e-3
+    assert (out.float() - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("ks,stride,padding", [(3, 1, "same"), (3, 2, "same"), (5, 1, "same"), (5, 2, "same"),
+                                               (3, 2, "symmetric"), (5, 2, "symmetric"), (3, 1, "valid")])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dwconv_bias_act_and_pool(ks, stride, padding, dtype):
+    ops = _ops()
+    B, H, W, C = 2, 19, 23, 136
+    g = torch.Generator(device="cuda").manual_seed(ks * 10 + stride)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(dtype)
+    wgt = torch.randn(ks * ks, C, device="cuda", generator=g) / ks
+    bias = torch.randn(C, device="cuda", generator=g)
+    pool = torch.zeros(B, C, device="cuda")
+    out = ops.dwconv_bias_act(x, wgt, bias, ks, stride, padding, act="swish", pool_sum=pool)
+    torch.cuda.synchronize()
+    xin = x.float().permute(0, 3, 1, 2)
+    if padding == "same":
+        oh, pt = ops.same_pad(H, ks, stride)
+        ow, pl = ops.same_pad(W, ks, stride)
+        tot_h = max((oh - 1) * stride + ks - H, 0)
+        tot_w = max((ow - 1) * stride + ks - W, 0)
+        xin = torch.nn.functional.pad(xin, (pl, tot_w - pl, pt, tot_h - pt))
+    elif padding == "symmetric":
+        pd = ((stride - 1) + (ks - 1)) // 2
+        xin = torch.nn.functional.pad(xin, (pd, pd, pd, pd))
+    wt = wgt.view(ks, ks, C).permute(2, 0, 1)[:, None]
+    y = torch.nn.functional.conv2d(xin, wt, bias, stride=stride, groups=C)
+    ref = (y * torch.sigmoid(y)).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    tol = 1e-4 if dtype == torch.float32 else 2.0 ** -8 * ref.abs().max().item() + 1e-3
+    assert (out.float() - ref).abs().max().item() < tol
+    pref = out.float().sum(dim=(1, 2))
+    assert (pool - pref).abs().max().item() < 1e-2 * max(1.0, pref.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_global_avg_pool(dtype):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(5, 7, 7, 1000, device="cuda", generator=g).to(dtype)
+    out = ops.global_avg_pool(x)
+    torch.cuda.synchronize()
+    assert (out - x.float().mean(dim=(1, 2))).abs().max().item() < 1e-5
