@@ -74,6 +74,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Samples taken before this call (warm-up) are dropped."""
+        self.skip = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -84,7 +88,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        lines = self.lines[getattr(self, "skip", 0):] or self.lines[-3:]
+        for line in lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -216,12 +221,14 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # started before the warm-up: nvidia-smi needs ~1 s before its first sample
     for _ in range(max(args.warmup, 3)):
         step(x_dev)
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     launches0 = ops.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

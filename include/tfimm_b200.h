@@ -89,9 +89,23 @@ int tfimm_b200_attention_bf16(const void* qkv, void* out, int B, int N, int H, i
 
 /* fp32 attention with optional additive bias[H,N,N] and mask[nmask,N,N] (window b uses mask b % nmask)
  * and optional probability output probs[B,H,N,N] (features["attn"], vit.py:163).
+ * row_map (optional, int32[nw_img*N]): window b reads/writes image (b / nw_img), token
+ * row_map[(b % nw_img)*N + j] -- the tf.roll + window_partition / window_reverse + tf.roll permutation of
+ * SwinTransformerBlock.call (swin.py:299-313) folded into addressing.
  * Covers vit.py:149-165 and swin.py:172-194 in precision="fp32". */
 int tfimm_b200_attention_f32(const float* qkv, float* out, const float* bias, const float* mask, int nmask,
-                             long B, int N, int H, int dh, float scale, float* probs, void* stream);
+                             long B, int N, int H, int dh, float scale, float* probs, const int* row_map,
+                             int nw_img, void* stream);
+
+/* Swin (shifted-)window attention, bf16, head_dim 32, N = window_size^2 <= 64 tokens per window:
+ * softmax(scale q k^T + bias[h] + mask) v per (window, head) with the cyclic shift and window
+ * partition/reverse folded into row addressing (row_map as above).  labels (optional, int32[nw_img*N]):
+ * region ids of the shifted-window mask; tokens with different ids get -100 added, exactly the
+ * attn_mask of swin.py:249-273.  qkv:(B*L, 3*H*dh) in token order, out:(B*L, H*dh), L = nw_img*N.
+ * Replaces swin.py:159-198 + 299-313. */
+int tfimm_b200_window_attention_bf16(const void* qkv, void* out, const float* bias, const int* row_map,
+                                     const int* labels, int B, int nw_img, int N, int H, int dh, float scale,
+                                     void* stream);
 
 /* Non-overlapping p x p patch gather (im2col of Conv2D(k=p, s=p, VALID)); out (B*H/p*W/p, Kpad),
  * column order (ky, kx, c), zero-padded to Kpad.  Optional fused create_preprocessing:
@@ -123,6 +137,29 @@ int tfimm_b200_dwconv_bias_act(const void* x, int dtype, const float* wgt, const
 /* Mean over the spatial axis: (B, HW, C) -> (B, C) fp32.  GlobalAveragePooling (convnext.py:433,
  * efficientnet.py:256, swin.py:456, layers/classifier.py:34). */
 int tfimm_b200_global_avg_pool(const void* x, int dtype, float* out, int B, int HW, int C, void* stream);
+
+/* im2col for dense k x k convolutions (stems, fused-MBConv / ResNet 3x3, 7x7) that then run as tcgen05
+ * GEMMs: out[(b,oy,ox), (ky,kx,c)] = x[b, oy*s+ky-pad_t, ox*s+kx-pad_l, c], zero outside / beyond k*k*C.
+ * Replaces the gather half of tf.keras.layers.Conv2D at efficientnet.py:216-222,
+ * efficientnet_blocks.py:482-497 (conv_exp), resnet.py:130-137,230-238,506-512. */
+int tfimm_b200_im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int ks,
+                      int stride, int pad_t, int pad_l, int Ho, int Wo, int Kpad, void* stream);
+
+/* SqueezeExcite gate from pooled sums: gate[b] = gate_act(W_e act(W_r mean[b] + b_r) + b_e), fp32.
+ * efficientnet_blocks.py:241-247 (mean -> conv_reduce -> act1 -> conv_expand -> gate), layers/attention.py:67-75.
+ * w_reduce:[rd][C], w_expand:[C][rd]. */
+int tfimm_b200_se_gate(const float* pooled_sum, float inv_hw, const float* w_reduce, const float* b_reduce,
+                       const float* w_expand, const float* b_expand, float* gate, int B, int C, int rd, int act,
+                       int gate_act, void* stream);
+
+/* x[b, p, c] *= gate[b, c] in place (the "x * x_se" of efficientnet_blocks.py:247). */
+int tfimm_b200_scale_channels(void* x, int dtype, const float* gate, int B, int HW, int C, void* stream);
+
+/* Window pooling on NHWC: mode 0 = max (ResNet stem MaxPool2D after ZeroPadding2D, resnet.py:536-539;
+ * padding is explicit and never wins), mode 1 = average over in-bounds cells (AveragePooling2D
+ * padding="same", resnet.py:299-301). */
+int tfimm_b200_pool2d(const void* x, int dtype, void* out, int B, int H, int W, int C, int ks, int stride,
+                      int pad_t, int pad_l, int Ho, int Wo, int mode, void* stream);
 
 /* Elementwise dtype conversion. */
 int tfimm_b200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream);

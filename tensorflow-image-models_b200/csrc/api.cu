@@ -51,7 +51,9 @@ int patch_merge_ln(const void*, int, const float*, const float*, void*, int, int
                    cudaStream_t);
 int attention_bf16(const void*, void*, int, int, int, int, float, cudaStream_t);
 int attention_f32(const float*, float*, const float*, const float*, int, long, int, int, int, float, float*,
-                  cudaStream_t);
+                  const int*, int, cudaStream_t);
+int window_attention_bf16(const void*, void*, const float*, const int*, const int*, int, int, int, int, int,
+                          float, cudaStream_t);
 int patchify(const void*, int, void*, int, int, int, int, int, int, int, float, const float*, const float*,
              cudaStream_t);
 int assemble_tokens(const void*, int, const float*, const float*, const float*, void*, int, int, int, int, int,
@@ -62,6 +64,11 @@ int dwconv_ln(const void*, int, const float*, const float*, const float*, const 
 int dwconv_bias_act(const void*, int, const float*, const float*, void*, float*, int, int, int, int, int, int,
                     int, int, int, int, int, cudaStream_t);
 int global_avg_pool(const void*, int, float*, int, int, int, cudaStream_t);
+int im2col(const void*, int, void*, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int se_gate(const float*, float, const float*, const float*, const float*, const float*, float*, int, int, int,
+            int, int, cudaStream_t);
+int scale_channels(void*, int, const float*, int, int, int, cudaStream_t);
+int pool2d(const void*, int, void*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 
 }  // namespace tfimm
 
@@ -109,8 +116,15 @@ int tfimm_b200_attention_bf16(const void* qkv, void* out, int B, int N, int H, i
 }
 
 int tfimm_b200_attention_f32(const float* qkv, float* out, const float* bias, const float* mask, int nmask,
-                             long B, int N, int H, int dh, float scale, float* probs, void* stream) {
-  return tfimm::attention_f32(qkv, out, bias, mask, nmask, B, N, H, dh, scale, probs, S(stream));
+                             long B, int N, int H, int dh, float scale, float* probs, const int* row_map,
+                             int nw_img, void* stream) {
+  return tfimm::attention_f32(qkv, out, bias, mask, nmask, B, N, H, dh, scale, probs, row_map, nw_img, S(stream));
+}
+
+int tfimm_b200_window_attention_bf16(const void* qkv, void* out, const float* bias, const int* row_map,
+                                     const int* labels, int B, int nw_img, int N, int H, int dh, float scale,
+                                     void* stream) {
+  return tfimm::window_attention_bf16(qkv, out, bias, row_map, labels, B, nw_img, N, H, dh, scale, S(stream));
 }
 
 int tfimm_b200_patchify(const void* img, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C,
@@ -143,6 +157,27 @@ int tfimm_b200_dwconv_bias_act(const void* x, int dtype, const float* wgt, const
 
 int tfimm_b200_global_avg_pool(const void* x, int dtype, float* out, int B, int HW, int C, void* stream) {
   return tfimm::global_avg_pool(x, dtype, out, B, HW, C, S(stream));
+}
+
+int tfimm_b200_im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int ks,
+                      int stride, int pad_t, int pad_l, int Ho, int Wo, int Kpad, void* stream) {
+  return tfimm::im2col(x, in_dtype, out, out_dtype, B, H, W, C, ks, stride, pad_t, pad_l, Ho, Wo, Kpad, S(stream));
+}
+
+int tfimm_b200_se_gate(const float* pooled_sum, float inv_hw, const float* w_reduce, const float* b_reduce,
+                       const float* w_expand, const float* b_expand, float* gate, int B, int C, int rd, int act,
+                       int gate_act, void* stream) {
+  return tfimm::se_gate(pooled_sum, inv_hw, w_reduce, b_reduce, w_expand, b_expand, gate, B, C, rd, act, gate_act,
+                        S(stream));
+}
+
+int tfimm_b200_scale_channels(void* x, int dtype, const float* gate, int B, int HW, int C, void* stream) {
+  return tfimm::scale_channels(x, dtype, gate, B, HW, C, S(stream));
+}
+
+int tfimm_b200_pool2d(const void* x, int dtype, void* out, int B, int H, int W, int C, int ks, int stride,
+                      int pad_t, int pad_l, int Ho, int Wo, int mode, void* stream) {
+  return tfimm::pool2d(x, dtype, out, B, H, W, C, ks, stride, pad_t, pad_l, Ho, Wo, mode, S(stream));
 }
 
 }  // extern "C"

@@ -217,7 +217,8 @@ int launch_vit_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, in
 __global__ void attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                      const float* __restrict__ bias, const float* __restrict__ mask,
                                      int nmask, long total_rows, int N, int H, int dh, float scale,
-                                     float* __restrict__ probs) {
+                                     float* __restrict__ probs, const int* __restrict__ row_map,
+                                     int nw_img) {
   extern __shared__ float sh[];
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -230,12 +231,17 @@ __global__ void attention_f32_kernel(const float* __restrict__ qkv, float* __res
   const int h = (int)(bh % H);
   const long b = bh / H;
   const long ld = 3L * H * dh;
-  const float* base = qkv + b * N * ld + (long)h * dh;
-  for (int d = lane; d < dh; d += 32) qs[d] = base[(long)n * ld + d] * scale;
+  // Token (b, j) lives in row b*N + j, or -- for Swin windows -- wherever the roll + window-partition
+  // permutation put it: image (b / nw_img), token row_map[(b % nw_img) * N + j] (swin.py:299-303).
+  const long row_base = row_map != nullptr ? (b / nw_img) * ((long)nw_img * N) : b * N;
+  const int* rmap = row_map != nullptr ? row_map + (b % nw_img) * (long)N : nullptr;
+  auto grow = [&](int j) -> long { return row_base + (rmap != nullptr ? rmap[j] : j); };
+  const float* base = qkv + (long)h * dh;
+  for (int d = lane; d < dh; d += 32) qs[d] = base[grow(n) * ld + d] * scale;
   __syncwarp();
   float mx = -INFINITY;
   for (int j = lane; j < N; j += 32) {
-    const float* kr = base + (long)j * ld + (long)H * dh;
+    const float* kr = base + grow(j) * ld + (long)H * dh;
     float acc = 0.f;
     for (int d = 0; d < dh; ++d) acc = fmaf(qs[d], kr[d], acc);
     if (bias != nullptr) acc += bias[((long)h * N + n) * N + j];
@@ -257,8 +263,8 @@ __global__ void attention_f32_kernel(const float* __restrict__ qkv, float* __res
     for (int j = lane; j < N; j += 32) probs[((bh * N) + n) * (long)N + j] = sc[j] * inv;
   for (int d = lane; d < dh; d += 32) {
     float acc = 0.f;
-    for (int j = 0; j < N; ++j) acc = fmaf(sc[j], base[(long)j * ld + 2L * H * dh + d], acc);
-    out[(b * N + n) * ((long)H * dh) + (long)h * dh + d] = acc * inv;
+    for (int j = 0; j < N; ++j) acc = fmaf(sc[j], base[grow(j) * ld + 2L * H * dh + d], acc);
+    out[grow(n) * ((long)H * dh) + (long)h * dh + d] = acc * inv;
   }
 }
 
@@ -289,7 +295,9 @@ int attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, floa
 }
 
 int attention_f32(const float* qkv, float* out, const float* bias, const float* mask, int nmask, long B,
-                  int N, int H, int dh, float scale, float* probs, cudaStream_t stream) {
+                  int N, int H, int dh, float scale, float* probs, const int* row_map, int nw_img,
+                  cudaStream_t stream) {
+  TFIMM_CHECK_ARG(row_map == nullptr || (nw_img > 0 && B % nw_img == 0), "attention_f32: bad window map");
   TFIMM_CHECK_ARG(B > 0 && N > 0 && H > 0 && dh > 0, "attention_f32: bad shape");
   const int warps = 4;
   const long total = B * H * N;
@@ -300,7 +308,7 @@ int attention_f32(const float* qkv, float* out, const float* bias, const float* 
   }
   const unsigned grid = (unsigned)((total + warps - 1) / warps);
   attention_f32_kernel<<<grid, warps * 32, smem, stream>>>(qkv, out, bias, mask, nmask > 0 ? nmask : 1, total,
-                                                          N, H, dh, scale, probs);
+                                                          N, H, dh, scale, probs, row_map, nw_img > 0 ? nw_img : 1);
   TFIMM_LAUNCH_OK("attention_f32_kernel");
   return kOk;
 }

@@ -84,33 +84,64 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   const bool warp_has_rows = (m0 + warp * 32) < N;
   float row_sum = 1.f;
   if (warp_has_rows) {
-    const int nchunks = npad >> 4;
-    float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 16), r);
-      tmem_ld_wait();
+    // Scores are consumed in 32-column chunks (the last one may be 16 wide); the load of chunk c+1 is
+    // in flight while chunk c is processed.
+    const int nfull = npad >> 5;           // 32-wide chunks
+    const bool tail16 = (npad & 16) != 0;  // one extra 16-wide chunk
+    const int nchunks = nfull + (tail16 ? 1 : 0);
+    auto issue = [&](int c, uint32_t (&r)[32]) {
+      if (c < nfull) {
+        tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), r);
+      } else {
+        uint32_t t16[16];
+        tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 32), t16);
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (c * 16 + j < N) mx = fmaxf(mx, __uint_as_float(r[j]));
+        for (int j = 0; j < 16; ++j) r[j] = t16[j];
+#pragma unroll
+        for (int j = 16; j < 32; ++j) r[j] = 0xff800000u;  // -inf
+      }
+    };
+    float mx = -INFINITY;
+    {
+      uint32_t r[32], cur[32];
+      issue(0, r);
+      for (int c = 0; c < nchunks; ++c) {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cur[j] = r[j];
+        if (c + 1 < nchunks) issue(c + 1, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < N) mx = fmaxf(mx, __uint_as_float(cur[j]));
+      }
     }
     const float moff = mx * scale_log2;
     row_sum = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 16), r);
-      tmem_ld_wait();
-      float pv[16];
+    {
+      uint32_t r[32], cur[32];
+      issue(0, r);
+      for (int c = 0; c < nchunks; ++c) {
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float e = ex2_approx(fmaf(__uint_as_float(r[j]), scale_log2, -moff));
-        pv[j] = (c * 16 + j < N) ? e : 0.f;
-        row_sum += pv[j];
+        for (int j = 0; j < 32; ++j) cur[j] = r[j];
+        if (c + 1 < nchunks) issue(c + 1, r);
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(cur[2 * j]), scale_log2, -moff));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(cur[2 * j + 1]), scale_log2, -moff));
+          const float p0 = (c * 32 + 2 * j < N) ? e0 : 0.f;
+          const float p1 = (c * 32 + 2 * j + 1 < N) ? e1 : 0.f;
+          row_sum += p0 + p1;
+          pk[j] = pack_bf16x2(p0, p1);
+        }
+        // P chunk c overwrites score columns [16c, 16c+16): all already consumed (<= chunk c)
+        uint32_t lo[8], hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { lo[j] = pk[j]; hi[j] = pk[8 + j]; }
+        tmem_st_32x32b_x8(t_row + (uint32_t)(c * 16), lo);
+        if (c < nfull) tmem_st_32x32b_x8(t_row + (uint32_t)(c * 16 + 8), hi);
       }
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(pv[2 * j], pv[2 * j + 1]);
-      tmem_st_32x32b_x8(t_row + (uint32_t)(c * 8), pk);
     }
     tmem_st_wait();
   }

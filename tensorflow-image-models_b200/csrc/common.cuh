@@ -103,6 +103,60 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x > 0.f ? x - h : -h;
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2: two fp32 FMAs per issued instruction) ----
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t splat2(float v) { return pack2(v, v); }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_fast on a pair: same formula, FMA-pipe work halved by FFMA2 (MUFU rcp/ex2 stay scalar).
+__device__ __forceinline__ uint64_t gelu_fast2(uint64_t x) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  const uint64_t ax = pack2(fabsf(x0), fabsf(x1));
+  float u0, u1;
+  unpack2(fma2(ax, splat2(0.3275911f * 0.70710678f), splat2(1.0f)), u0, u1);
+  const uint64_t t = pack2(rcp_approx(u0), rcp_approx(u1));
+  uint64_t p = fma2(splat2(0.5f * 1.061405429f), t, splat2(0.5f * -1.453152027f));
+  p = fma2(p, t, splat2(0.5f * 1.421413741f));
+  p = fma2(p, t, splat2(0.5f * -0.284496736f));
+  p = fma2(p, t, splat2(0.5f * 0.254829592f));
+  p = mul2(p, t);  // 0.5 * erfc(|x|/sqrt2) * exp(x^2/2)
+  float z0, z1;
+  unpack2(mul2(mul2(ax, splat2(-0.72134752044448170368f)), ax), z0, z1);
+  const uint64_t e = pack2(ex2_approx(z0), ex2_approx(z1));
+  const uint64_t h = mul2(mul2(p, e), ax);  // |x| * Phi(-|x|)
+  // gelu(x) = relu(x) - h
+  return fma2(h, splat2(-1.0f), pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+__device__ __forceinline__ uint64_t swish_fast2(uint64_t x) {
+  float z0, z1;
+  unpack2(mul2(x, splat2(-1.4426950408889634f)), z0, z1);
+  float d0, d1;
+  unpack2(add2(pack2(ex2_approx(z0), ex2_approx(z1)), splat2(1.0f)), d0, d1);
+  return mul2(x, pack2(rcp_approx(d0), rcp_approx(d1)));
+}
+
 template <bool kPrecise>
 __device__ __forceinline__ float gelu_erf(float x) {
   if constexpr (kPrecise) {

@@ -246,7 +246,223 @@ __global__ void global_avg_pool_kernel(const T* __restrict__ x, float* __restric
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// im2col for dense k x k convolutions that are then run as tcgen05 GEMMs
+// ----------------------------------------------------------------------------------------------
+// out[(b, oy, ox), (ky, kx, c)] = x[b, oy*s + ky - pad_t, ox*s + kx - pad_l, c] (0 outside), columns padded
+// with zeros to Kpad.  Column order == TF conv kernel (kh, kw, cin, :) flattened.
+template <typename InT, typename OutT>
+__global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out, int B, int H, int W, int C,
+                              int Ho, int Wo, int ks, int stride, int pad_t, int pad_l, int Kpad) {
+  const int K = ks * ks * C;
+  const int chunks = Kpad >> 3;
+  const long total = (long)B * Ho * Wo * chunks;
+  const bool vec = (C & 7) == 0;  // 8 consecutive columns stay inside one (ky, kx) pixel
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % chunks);
+    const long m = idx / chunks;
+    const int ox = (int)(m % Wo);
+    const long t = m / Wo;
+    const int oy = (int)(t % Ho);
+    const long b = t / Ho;
+    const int k0 = ch * 8;
+    float v[8];
+    if (vec) {
+      const int tap = k0 / C, c = k0 % C;
+      const int ky = tap / ks, kx = tap % ks;
+      const int iy = oy * stride + ky - pad_t, ix = ox * stride + kx - pad_l;
+      if (k0 < K && iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        ld8(x + ((b * H + iy) * W + ix) * (long)C + c, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j;
+        float val = 0.f;
+        if (k < K) {
+          const int tap = k / C, c = k % C;
+          const int ky = tap / ks, kx = tap % ks;
+          const int iy = oy * stride + ky - pad_t, ix = ox * stride + kx - pad_l;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = ld_as_float(x + ((b * H + iy) * W + ix) * (long)C + c);
+        }
+        v[j] = val;
+      }
+    }
+    st8(out + m * Kpad + k0, v);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// squeeze-excite gate: pooled sums -> 1x1 conv (bias) -> act -> 1x1 conv (bias) -> gate act
+// ----------------------------------------------------------------------------------------------
+// One CTA per image.  pooled_sum[b][C] (sum over pixels), w_reduce[rd][C], w_expand[C][rd], fp32.
+__global__ void se_gate_kernel(const float* __restrict__ pooled_sum, float inv_hw,
+                               const float* __restrict__ w_reduce, const float* __restrict__ b_reduce,
+                               const float* __restrict__ w_expand, const float* __restrict__ b_expand,
+                               float* __restrict__ gate, int C, int rd, int act, int gate_act) {
+  extern __shared__ float sh[];
+  float* mean = sh;        // [C]
+  float* hid = sh + C;     // [rd]
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pooled_sum[(long)b * C + c] * inv_hw;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  for (int r = warp; r < rd; r += warps) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(mean[c], w_reduce[(long)r * C + c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) hid[r] = apply_act<true>(acc + b_reduce[r], act);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = b_expand[c];
+    for (int r = 0; r < rd; ++r) acc = fmaf(hid[r], w_expand[(long)c * rd + r], acc);
+    gate[(long)b * C + c] = apply_act<true>(acc, gate_act);
+  }
+}
+
+// x[b, p, c] *= gate[b, c]   (in place; 8 channels per thread)
+template <typename T>
+__global__ void scale_channels_kernel(T* __restrict__ x, const float* __restrict__ gate, long total_chunks,
+                                      int HW, int C) {
+  const int cpr = C >> 3;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_chunks;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % cpr);
+    const long row = idx / cpr;
+    const long b = row / HW;
+    float v[8], g[8];
+    ld8(x + row * C + ch * 8, v);
+    ld8(gate + b * C + ch * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= g[j];
+    st8(x + row * C + ch * 8, v);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// spatial pooling windows (ResNet stem max-pool, "avg-down" shortcuts)
+// ----------------------------------------------------------------------------------------------
+// mode 0: max (padding acts as -inf), mode 1: average over the in-bounds cells only (TF "same").
+template <typename T>
+__global__ void pool2d_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int Ho,
+                              int Wo, int ks, int stride, int pad_t, int pad_l, int mode) {
+  const int cpr = C >> 3;
+  const long total = (long)B * Ho * Wo * cpr;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % cpr);
+    const long m = idx / cpr;
+    const int ox = (int)(m % Wo);
+    const long t = m / Wo;
+    const int oy = (int)(t % Ho);
+    const long b = t / Ho;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = mode == 0 ? -INFINITY : 0.f;
+    int cnt = 0;
+    for (int ky = 0; ky < ks; ++ky) {
+      const int iy = oy * stride + ky - pad_t;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < ks; ++kx) {
+        const int ix = ox * stride + kx - pad_l;
+        if (ix < 0 || ix >= W) continue;
+        float v[8];
+        ld8(x + ((b * H + iy) * W + ix) * (long)C + ch * 8, v);
+        ++cnt;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = mode == 0 ? fmaxf(acc[j], v[j]) : acc[j] + v[j];
+      }
+    }
+    if (mode == 1) {
+      const float inv = 1.0f / (float)max(cnt, 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    }
+    st8(out + m * C + ch * 8, acc);
+  }
+}
+
+inline unsigned conv_grid_for(long total, int threads) {
+  long blocks = (total + threads - 1) / threads;
+  const long cap = (long)sm_count() * 16;
+  return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
 }  // namespace
+
+int im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int ks, int stride,
+           int pad_t, int pad_l, int Ho, int Wo, int Kpad, cudaStream_t stream) {
+  TFIMM_CHECK_ARG(B > 0 && ks > 0 && stride > 0 && Ho > 0 && Wo > 0, "im2col: bad geometry");
+  TFIMM_CHECK_ARG(Kpad % 8 == 0 && Kpad >= ks * ks * C, "im2col: Kpad must be a multiple of 8 and >= k*k*C");
+  const long total = (long)B * Ho * Wo * (Kpad / 8);
+  const unsigned grid = conv_grid_for(total, 256);
+#define TFIMM_I2C(IN, OUT)                                                                              \
+  im2col_kernel<IN, OUT><<<grid, 256, 0, stream>>>(reinterpret_cast<const IN*>(x), reinterpret_cast<OUT*>(out), \
+                                                  B, H, W, C, Ho, Wo, ks, stride, pad_t, pad_l, Kpad)
+  if (in_dtype == kF32 && out_dtype == kBF16) TFIMM_I2C(float, __nv_bfloat16);
+  else if (in_dtype == kBF16 && out_dtype == kBF16) TFIMM_I2C(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == kF32 && out_dtype == kF32) TFIMM_I2C(float, float);
+  else {
+    set_last_error("im2col: unsupported dtype combination in=%d out=%d", in_dtype, out_dtype);
+    return kInvalidArgument;
+  }
+#undef TFIMM_I2C
+  TFIMM_LAUNCH_OK("im2col_kernel");
+  return kOk;
+}
+
+int se_gate(const float* pooled_sum, float inv_hw, const float* w_reduce, const float* b_reduce,
+            const float* w_expand, const float* b_expand, float* gate, int B, int C, int rd, int act, int gate_act,
+            cudaStream_t stream) {
+  TFIMM_CHECK_ARG(B > 0 && C > 0 && rd > 0, "se_gate: bad shape");
+  const size_t smem = (size_t)(C + rd) * sizeof(float);
+  TFIMM_CHECK_ARG(smem <= 48 * 1024, "se_gate: C + rd too large (%d + %d)", C, rd);
+  se_gate_kernel<<<B, 256, smem, stream>>>(pooled_sum, inv_hw, w_reduce, b_reduce, w_expand, b_expand, gate, C, rd,
+                                           act, gate_act);
+  TFIMM_LAUNCH_OK("se_gate_kernel");
+  return kOk;
+}
+
+int scale_channels(void* x, int dtype, const float* gate, int B, int HW, int C, cudaStream_t stream) {
+  TFIMM_CHECK_ARG(B > 0 && HW > 0 && C > 0 && C % 8 == 0, "scale_channels: need C%%8==0 (C=%d)", C);
+  const long total = (long)B * HW * (C / 8);
+  const unsigned grid = conv_grid_for(total, 256);
+  if (dtype == kBF16)
+    scale_channels_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(x), gate, total, HW, C);
+  else if (dtype == kF32)
+    scale_channels_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<float*>(x), gate, total, HW, C);
+  else {
+    set_last_error("scale_channels: dtype must be bf16 or f32");
+    return kInvalidArgument;
+  }
+  TFIMM_LAUNCH_OK("scale_channels_kernel");
+  return kOk;
+}
+
+int pool2d(const void* x, int dtype, void* out, int B, int H, int W, int C, int ks, int stride, int pad_t,
+           int pad_l, int Ho, int Wo, int mode, cudaStream_t stream) {
+  TFIMM_CHECK_ARG(B > 0 && C % 8 == 0 && ks > 0 && stride > 0, "pool2d: need C%%8==0 (C=%d)", C);
+  TFIMM_CHECK_ARG(mode == 0 || mode == 1, "pool2d: mode must be 0 (max) or 1 (avg)");
+  const long total = (long)B * Ho * Wo * (C / 8);
+  const unsigned grid = conv_grid_for(total, 256);
+  if (dtype == kBF16)
+    pool2d_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out),
+                                            B, H, W, C, Ho, Wo, ks, stride, pad_t, pad_l, mode);
+  else if (dtype == kF32)
+    pool2d_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(out), B, H, W,
+                                            C, Ho, Wo, ks, stride, pad_t, pad_l, mode);
+  else {
+    set_last_error("pool2d: dtype must be bf16 or f32");
+    return kInvalidArgument;
+  }
+  TFIMM_LAUNCH_OK("pool2d_kernel");
+  return kOk;
+}
 
 int dwconv_ln(const void* x, int in_dtype, const float* wgt, const float* bias, const float* gamma,
               const float* beta, void* out, int out_dtype, int B, int H, int W, int C, int ks, float eps,

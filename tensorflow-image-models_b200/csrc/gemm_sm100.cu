@@ -9,16 +9,16 @@
 // resnet.py:220-248) plus the patchify convolutions once their input has been
 // gathered (layers/transformers.py:131-139, convnext.py:259-266,319-326).
 //
-// Design (one persistent CTA per SM, warp-specialised):
+// Design (one persistent CTA per SM, warp-specialised, 320 threads):
 //   warp 0      TMA producer: A/W tiles -> 128B-swizzled smem ring (mbarrier full/empty)
 //   warp 1      MMA issuer: tcgen05.mma 128 x BLOCK_N x 16, fp32 accumulators in TMEM,
 //               two accumulator stages so the epilogue of tile i overlaps the MMAs of i+1
-//   warps 2..5  epilogue: tcgen05.ld -> bias/act/gamma/residual in registers ->
-//               swizzled smem slab -> TMA store (one 32-row slab per warp, so no
-//               cross-warp barrier).  The residual tile is TMA-loaded into the same
-//               slab and may alias the output (in-place residual stream).
+//   warps 2..9  epilogue, two warps per TMEM lane quarter taking alternate 128-byte column
+//               chunks: tcgen05.ld -> bias/act/gamma (FFMA2) -> + residual -> swizzled smem slab
+//               -> TMA store.  Each warp owns its 32-row slab, so there is no cross-warp barrier;
+//               the residual chunk is TMA-prefetched into the same slab while the accumulator is
+//               being loaded and activated, and may alias the output (in-place residual stream).
 #include "common.cuh"
-
 
 namespace tfimm {
 namespace {
@@ -26,10 +26,9 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kNumEpiWarps = 4;
+constexpr int kNumEpiWarps = 8;
 constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
-constexpr int kSlabBytes = 32 * 128;  // 32 rows x 128 B
-constexpr int kSlabBufs = 2;
+constexpr int kSlabBytes = 32 * 128;  // 32 rows x 128 B, one per epilogue warp
 constexpr int kAccStages = 2;
 
 template <int BLOCK_N>
@@ -38,8 +37,8 @@ struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
-  static constexpr int kSlabTotal = kNumEpiWarps * kSlabBufs * kSlabBytes;
-  static constexpr int kNumBarriers = 2 * kStages + 2 * kAccStages + kNumEpiWarps * kSlabBufs;
+  static constexpr int kSlabTotal = kNumEpiWarps * kSlabBytes;
+  static constexpr int kNumBarriers = 2 * kStages + 2 * kAccStages + kNumEpiWarps;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kSlabTotal + kNumBarriers * 8 + 16 + 1024 /*alignment slack*/;
   static constexpr uint32_t kTmemCols = kAccStages * BLOCK_N;  // 512 / 256 / 128
@@ -52,6 +51,56 @@ struct GemmParams {
   int act;
   int has_res;
 };
+
+// v[j] (+ or *)= vec[n0 + j] on packed pairs; full chunks use 16-byte loads.
+template <int CH, bool kMul>
+__device__ __forceinline__ void apply_vec(uint64_t (&v)[CH / 2], const float* __restrict__ vec, int n0, int N) {
+  if (n0 + CH <= N) {
+#pragma unroll
+    for (int j = 0; j < CH; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(vec + n0 + j));
+      if (kMul) {
+        v[j / 2] = mul2(v[j / 2], pack2(b4.x, b4.y));
+        v[j / 2 + 1] = mul2(v[j / 2 + 1], pack2(b4.z, b4.w));
+      } else {
+        v[j / 2] = add2(v[j / 2], pack2(b4.x, b4.y));
+        v[j / 2 + 1] = add2(v[j / 2 + 1], pack2(b4.z, b4.w));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CH; j += 2) {
+      const float neutral = kMul ? 1.f : 0.f;
+      const float b0 = (n0 + j < N) ? __ldg(vec + n0 + j) : neutral;
+      const float b1 = (n0 + j + 1 < N) ? __ldg(vec + n0 + j + 1) : neutral;
+      v[j / 2] = kMul ? mul2(v[j / 2], pack2(b0, b1)) : add2(v[j / 2], pack2(b0, b1));
+    }
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ void apply_act_pairs(uint64_t (&v)[NP], int act) {
+  switch (act) {
+    case kActGelu:
+#pragma unroll
+      for (int j = 0; j < NP; ++j) v[j] = gelu_fast2(v[j]);
+      break;
+    case kActSwish:
+#pragma unroll
+      for (int j = 0; j < NP; ++j) v[j] = swish_fast2(v[j]);
+      break;
+    case kActNone:
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        float a, b;
+        unpack2(v[j], a, b);
+        v[j] = pack2(apply_act<false>(a, act), apply_act<false>(b, act));
+      }
+      break;
+  }
+}
 
 template <int BLOCK_N, typename OutT>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -74,9 +123,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   auto empty_bar = [&](int s) { return smem_bars + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return smem_bars + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return smem_bars + 8u * (2 * kStages + kAccStages + s); };
-  auto res_bar = [&](int w, int b) {
-    return smem_bars + 8u * (2 * kStages + 2 * kAccStages + w * kSlabBufs + b);
-  };
+  auto res_bar = [&](int w) { return smem_bars + 8u * (2 * kStages + 2 * kAccStages + w); };
   const uint32_t tmem_ptr_smem = smem_bars + 8u * Cfg::kNumBarriers;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of smem_base
 
@@ -96,8 +143,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), kNumEpiWarps);
     }
-    for (int w = 0; w < kNumEpiWarps; ++w)
-      for (int b = 0; b < kSlabBufs; ++b) mbar_init(res_bar(w, b), 1);
+    for (int w = 0; w < kNumEpiWarps; ++w) mbar_init(res_bar(w), 1);
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
@@ -165,34 +211,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else {
     // -------------------------------- epilogue --------------------------------
+    const int ew = warp_idx - 2;         // 0..7: slab / residual-barrier owner
     const int q = warp_idx & 3;          // TMEM lane quarter this warp may access
-    const int ew = warp_idx - 2;         // slab owner index 0..3
-    const uint32_t slab0 = smem_slabs + (uint32_t)(ew * kSlabBufs) * kSlabBytes;
-    uint8_t* slab0_gen = smem_gen + (slab0 - smem_base);
+    const int grp = ew >> 2;             // which half of the column chunks this warp takes
+    const uint32_t slab = smem_slabs + (uint32_t)ew * kSlabBytes;
+    uint8_t* my_row = smem_gen + (slab - smem_base) + lane * 128;
+    const int sw = lane & 7;             // TMA SWIZZLE_128B: 16-byte chunk j of row r lives at j ^ (r & 7)
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t cc = 0;  // running chunk counter (selects slab buffer + residual barrier parity)
+    uint32_t cc = 0;  // chunks processed by this warp (residual barrier parity)
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / num_n_tiles, n_blk = t % num_n_tiles;
       const int row0 = m_blk * kBlockM + q * 32;
+      const int cols_left = p.N - n_blk * BLOCK_N;
+      const int nvalid = cols_left >= BLOCK_N ? NCH : (cols_left + CH - 1) / CH;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        const int n0 = n_blk * BLOCK_N + c * CH;
-        if (n0 >= p.N) break;
-        const int buf = (int)(cc & 1u);
-        const uint32_t slab = slab0 + (uint32_t)buf * kSlabBytes;
-        uint8_t* slab_gen = slab0_gen + buf * kSlabBytes;
-        // The store that last read this buffer was issued two chunks ago.
-        if (lane == 0) tma_store_wait_read<1>();
+      if (grp >= nvalid) {
+        // nothing to read for this warp in this tile: hand the accumulator back right away
         __syncwarp();
-        if (p.has_res && lane == 0) {
-          mbar_expect_tx(res_bar(ew, buf), kSlabBytes);
-          tma_load_2d(slab, &tmap_r, res_bar(ew, buf), n0, row0);
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+#pragma unroll 1
+      for (int c = grp; c < nvalid; c += 2) {
+        const int n0 = n_blk * BLOCK_N + c * CH;
+        // the previous store of this warp must have finished reading the slab
+        if (lane == 0) {
+          tma_store_wait_read<0>();
+          if (p.has_res) {
+            mbar_expect_tx(res_bar(ew), kSlabBytes);
+            tma_load_2d(slab, &tmap_r, res_bar(ew), n0, row0);
+          }
         }
-        float v[CH];
+        __syncwarp();
+        uint64_t v[CH / 2];
         {
           uint32_t r[32];
 #pragma unroll
@@ -200,62 +253,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * CH + h * 32), r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[h * 32 + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 16; ++j)
+              v[h * 16 + j] = pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
           }
         }
-        if (c == NCH - 1 || n0 + CH >= p.N) {
-          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+        if (c + 2 >= nvalid) {
+          // all TMEM reads of this accumulator stage by this warp are done
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        const bool full_chunk = (n0 + CH <= p.N);
-        if (p.bias != nullptr) {
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < CH; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
-          }
-        }
-        if (p.act != kActNone) apply_act_array<false>(v, p.act);
-        if (p.gamma != nullptr) {
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < CH; j += 4) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j));
-              v[j] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (n0 + j < p.N) v[j] *= __ldg(p.gamma + n0 + j);
-          }
-        }
-        // slab row = lane; 16-byte chunk j lives at ((j ^ (lane & 7)) << 4) (TMA SWIZZLE_128B)
-        uint8_t* my_row = slab_gen + lane * 128;
-        const int sw = lane & 7;
+        if (p.bias != nullptr) apply_vec<CH, false>(v, p.bias, n0, p.N);
+        apply_act_pairs(v, p.act);
+        if (p.gamma != nullptr) apply_vec<CH, true>(v, p.gamma, n0, p.N);
         if (p.has_res) {
-          mbar_wait(res_bar(ew, buf), (cc >> 1) & 1u);
+          mbar_wait(res_bar(ew), cc & 1u);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
             if constexpr (sizeof(OutT) == 2) {
-              float2 f;
-              f = unpack_bf16x2(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
-              f = unpack_bf16x2(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
-              f = unpack_bf16x2(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
-              f = unpack_bf16x2(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+              const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
+              const float2 f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[4 * j + 0] = add2(v[4 * j + 0], pack2(f0.x, f0.y));
+              v[4 * j + 1] = add2(v[4 * j + 1], pack2(f1.x, f1.y));
+              v[4 * j + 2] = add2(v[4 * j + 2], pack2(f2.x, f2.y));
+              v[4 * j + 3] = add2(v[4 * j + 3], pack2(f3.x, f3.y));
             } else {
-              v[4 * j + 0] += __uint_as_float(u.x);
-              v[4 * j + 1] += __uint_as_float(u.y);
-              v[4 * j + 2] += __uint_as_float(u.z);
-              v[4 * j + 3] += __uint_as_float(u.w);
+              v[2 * j + 0] = add2(v[2 * j + 0], pack2(__uint_as_float(u.x), __uint_as_float(u.y)));
+              v[2 * j + 1] = add2(v[2 * j + 1], pack2(__uint_as_float(u.z), __uint_as_float(u.w)));
             }
           }
         }
@@ -263,15 +288,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int j = 0; j < 8; ++j) {
           uint4 u;
           if constexpr (sizeof(OutT) == 2) {
-            u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-            u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            float a0, a1, a2, a3, a4, a5, a6, a7;
+            unpack2(v[4 * j + 0], a0, a1);
+            unpack2(v[4 * j + 1], a2, a3);
+            unpack2(v[4 * j + 2], a4, a5);
+            unpack2(v[4 * j + 3], a6, a7);
+            u.x = pack_bf16x2(a0, a1);
+            u.y = pack_bf16x2(a2, a3);
+            u.z = pack_bf16x2(a4, a5);
+            u.w = pack_bf16x2(a6, a7);
           } else {
-            u.x = __float_as_uint(v[4 * j + 0]);
-            u.y = __float_as_uint(v[4 * j + 1]);
-            u.z = __float_as_uint(v[4 * j + 2]);
-            u.w = __float_as_uint(v[4 * j + 3]);
+            float a0, a1, a2, a3;
+            unpack2(v[2 * j + 0], a0, a1);
+            unpack2(v[2 * j + 1], a2, a3);
+            u.x = __float_as_uint(a0);
+            u.y = __float_as_uint(a1);
+            u.z = __float_as_uint(a2);
+            u.w = __float_as_uint(a3);
           }
           *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = u;
         }

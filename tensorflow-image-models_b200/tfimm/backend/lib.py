@@ -33,13 +33,18 @@ SIGNATURES = {
     "tfimm_b200_layernorm_patch2x2": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "tfimm_b200_patch_merge_ln": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "tfimm_b200_attention_bf16": [_P, _P, _I, _I, _I, _I, _F, _P],
-    "tfimm_b200_attention_f32": [_P, _P, _P, _P, _I, _L, _I, _I, _I, _F, _P, _P],
+    "tfimm_b200_attention_f32": [_P, _P, _P, _P, _I, _L, _I, _I, _I, _F, _P, _P, _I, _P],
+    "tfimm_b200_window_attention_bf16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "tfimm_b200_patchify": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
     "tfimm_b200_assemble_tokens": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "tfimm_b200_cast": [_P, _I, _P, _I, _L, _P],
     "tfimm_b200_dwconv_ln": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "tfimm_b200_dwconv_bias_act": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "tfimm_b200_global_avg_pool": [_P, _I, _P, _I, _I, _I, _P],
+    "tfimm_b200_im2col": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "tfimm_b200_se_gate": [_P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "tfimm_b200_scale_channels": [_P, _I, _P, _I, _I, _I, _P],
+    "tfimm_b200_pool2d": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
 }
 _SPECIAL = {
     "tfimm_b200_version": ([], _c.c_char_p),

@@ -135,19 +135,20 @@ def patch_merge_ln(x, gamma, beta, eps, out_dtype):
     return out
 
 
-def attention(qkv, B, N, H, dh, scale, bias=None, mask=None, probs=None):
-    """softmax(scale q k^T [+bias +mask]) v from packed qkv (B*N, 3*H*dh) -> (B*N, H*dh)."""
-    _cuda(qkv, bias, mask, probs)
+def attention(qkv, B, N, H, dh, scale, bias=None, mask=None, probs=None, row_map=None, nw_img=0):
+    """softmax(scale q k^T [+bias +mask]) v from packed qkv (B*N, 3*H*dh) -> (B*N, H*dh).
+    row_map/nw_img (fp32 only): Swin window permutation folded into addressing."""
+    _cuda(qkv, bias, mask, probs, row_map)
     assert qkv.shape == (B * N, 3 * H * dh) and qkv.is_contiguous()
     out = torch.empty((B * N, H * dh), device=qkv.device, dtype=qkv.dtype)
-    if qkv.dtype == torch.bfloat16 and bias is None and mask is None and probs is None:
+    if qkv.dtype == torch.bfloat16 and bias is None and mask is None and probs is None and row_map is None:
         _call("tfimm_b200_attention_bf16", qkv.data_ptr(), out.data_ptr(), B, N, H, dh, float(scale), _stream(),
               flops=4.0 * B * H * N * N * dh, nbytes=_nbytes(qkv, out))
     elif qkv.dtype == torch.float32:
         nmask = mask.shape[0] if mask is not None else 1
         _call("tfimm_b200_attention_f32", qkv.data_ptr(), out.data_ptr(), _ptr(bias), _ptr(mask), nmask, B, N,
-              H, dh, float(scale), _ptr(probs), _stream(), flops=4.0 * B * H * N * N * dh,
-              nbytes=_nbytes(qkv, out, probs))
+              H, dh, float(scale), _ptr(probs), _ptr(row_map), nw_img, _stream(),
+              flops=4.0 * B * H * N * N * dh, nbytes=_nbytes(qkv, out, probs))
     else:
         raise _lib.KernelLibraryError("attention: unsupported dtype / option combination")
     return out
@@ -242,4 +243,79 @@ def global_avg_pool(x):
     out = torch.empty((B, C), device=x.device, dtype=torch.float32)
     _call("tfimm_b200_global_avg_pool", x.data_ptr(), _code(x), out.data_ptr(), B, HW, C, _stream(),
           nbytes=_nbytes(x, out))
+    return out
+
+
+def window_attention(qkv, bias, row_map, labels, B, nw_img, N, H, dh, scale):
+    """Swin (shifted-)window attention on token-ordered qkv (B*nw_img*N, 3*H*dh) -> (B*nw_img*N, H*dh)."""
+    _cuda(qkv, bias, row_map, labels)
+    assert qkv.shape == (B * nw_img * N, 3 * H * dh) and qkv.is_contiguous() and qkv.dtype == torch.bfloat16
+    assert row_map.dtype == torch.int32 and (labels is None or labels.dtype == torch.int32)
+    out = torch.empty((B * nw_img * N, H * dh), device=qkv.device, dtype=qkv.dtype)
+    _call("tfimm_b200_window_attention_bf16", qkv.data_ptr(), out.data_ptr(), bias.data_ptr(), row_map.data_ptr(),
+          _ptr(labels), B, nw_img, N, H, dh, float(scale), _stream(),
+          flops=4.0 * B * nw_img * H * N * N * dh, nbytes=_nbytes(qkv, out))
+    return out
+
+
+def conv_geometry(H, W, ks, stride, padding):
+    """(Ho, Wo, pad_top, pad_left) for "same" (TF, asymmetric) | "symmetric" (PyTorch-style) | "valid" | int."""
+    if padding == "same":
+        Ho, pt = same_pad(H, ks, stride)
+        Wo, pl = same_pad(W, ks, stride)
+        return Ho, Wo, pt, pl
+    if padding == "symmetric":
+        pd = ((stride - 1) + (ks - 1)) // 2
+    elif padding == "valid":
+        pd = 0
+    else:
+        pd = int(padding)
+    return (H + 2 * pd - ks) // stride + 1, (W + 2 * pd - ks) // stride + 1, pd, pd
+
+
+def im2col(x, ks, stride, padding, out_dtype):
+    """x: (B,H,W,C) -> ((B*Ho*Wo, ceil8(ks*ks*C)), Ho, Wo)."""
+    _cuda(x)
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    Ho, Wo, pt, pl = conv_geometry(H, W, ks, stride, padding)
+    Kpad = (ks * ks * C + 7) // 8 * 8
+    out = torch.empty((B * Ho * Wo, Kpad), device=x.device, dtype=out_dtype)
+    _call("tfimm_b200_im2col", x.data_ptr(), _code(x), out.data_ptr(), _code(out), B, H, W, C, ks, stride, pt, pl,
+          Ho, Wo, Kpad, _stream(), nbytes=_nbytes(x, out))
+    return out, Ho, Wo
+
+
+def se_gate(pooled_sum, hw, w_reduce, b_reduce, w_expand, b_expand, act, gate_act="sigmoid"):
+    """pooled_sum: (B, C) fp32 sums over hw pixels -> gate (B, C) fp32."""
+    _cuda(pooled_sum, w_reduce, b_reduce, w_expand, b_expand)
+    B, C = pooled_sum.shape
+    rd = w_reduce.shape[0]
+    gate = torch.empty((B, C), device=pooled_sum.device, dtype=torch.float32)
+    _call("tfimm_b200_se_gate", pooled_sum.data_ptr(), 1.0 / float(hw), w_reduce.data_ptr(), b_reduce.data_ptr(),
+          w_expand.data_ptr(), b_expand.data_ptr(), gate.data_ptr(), B, C, rd, act_code(act), act_code(gate_act),
+          _stream(), flops=4.0 * B * C * rd, nbytes=_nbytes(pooled_sum, gate))
+    return gate
+
+
+def scale_channels_(x, gate):
+    """In place: x[b, ..., c] *= gate[b, c]."""
+    _cuda(x, gate)
+    assert x.is_contiguous()
+    B, C = gate.shape
+    HW = x.numel() // (B * C)
+    _call("tfimm_b200_scale_channels", x.data_ptr(), _code(x), gate.data_ptr(), B, HW, C, _stream(),
+          nbytes=2 * _nbytes(x))
+    return x
+
+
+def pool2d(x, ks, stride, padding, mode):
+    """mode "max" | "avg" on (B,H,W,C); padding as in conv_geometry."""
+    _cuda(x)
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    Ho, Wo, pt, pl = conv_geometry(H, W, ks, stride, padding)
+    out = torch.empty((B, Ho, Wo, C), device=x.device, dtype=x.dtype)
+    _call("tfimm_b200_pool2d", x.data_ptr(), _code(x), out.data_ptr(), B, H, W, C, ks, stride, pt, pl, Ho, Wo,
+          0 if mode == "max" else 1, _stream(), nbytes=_nbytes(x, out))
     return out

@@ -325,3 +325,38 @@ def test_global_avg_pool(dtype):
     out = ops.global_avg_pool(x)
     torch.cuda.synchronize()
     assert (out - x.float().mean(dim=(1, 2))).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("h,w,ws,shift,H", [(14, 14, 7, 3, 4), (14, 14, 7, 0, 4), (28, 21, 7, 3, 2), (8, 8, 4, 2, 3), (7, 7, 7, 0, 8)])
+def test_window_attention_bf16(h, w, ws, shift, H):
+    """Index-folded shifted-window attention vs explicit roll / partition / mask in torch."""
+    from tfimm.architectures.swin import window_tables
+
+    ops = _ops()
+    B, dh = 3, 32
+    n, nw, C = ws * ws, (h // ws) * (w // ws), H * 32
+    g = torch.Generator(device="cuda").manual_seed(h * w + shift)
+    qkv = (torch.randn(B * h * w, 3 * C, device="cuda", generator=g) * 1.2).to(torch.bfloat16)
+    bias = torch.randn(H, n, n, device="cuda", generator=g)
+    row_map, labels = window_tables(h, w, ws, shift)
+    rm = torch.from_numpy(row_map).cuda()
+    lab = torch.from_numpy(labels).cuda() if labels is not None else None
+    out = ops.window_attention(qkv, bias, rm, lab, B, nw, n, H, dh, dh ** -0.5)
+    torch.cuda.synchronize()
+    # reference: explicit data movement
+    x = qkv.float().view(B, h, w, 3 * C)
+    xs = torch.roll(x, (-shift, -shift), (1, 2))
+    xw = xs.view(B, h // ws, ws, w // ws, ws, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(B * nw, n, 3 * C)
+    mask = None
+    if labels is not None:
+        lb = torch.from_numpy(labels).cuda().view(nw, n)
+        mask = torch.where(lb[:, None, :] != lb[:, :, None], -100.0, 0.0)
+    ow, _ = _attn_ref(xw.reshape(B * nw * n, 3 * C), B * nw, n, H, dh, dh ** -0.5, bias, mask)
+    ow = ow.view(B, h // ws, w // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, h, w, C)
+    ref = torch.roll(ow, (shift, shift), (1, 2)).reshape(B * h * w, C)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2, err
+    # fp32 kernel with the same row map
+    out32 = ops.attention(qkv.float(), B * nw, n, H, dh, dh ** -0.5, bias=bias, mask=mask, row_map=rm, nw_img=nw)
+    torch.cuda.synchronize()
+    assert (out32 - ref).abs().max().item() < 2e-5

@@ -152,3 +152,40 @@ def test_convnext_return_features():
     assert list(feats.keys()) == list(ofeats.keys()) == model.feature_names
     for k in ("stem", "stage_1/downsample", "stage_2/block_3", "conv_features", "features", "logits"):
         assert _nerr(feats[k], ofeats[k])[0] < 5e-5, k
+
+
+@pytest.mark.parametrize("name,overrides", [("swin_tiny_patch4_window7_224", {}),
+                                            ("swin_tiny_patch4_window7_224", {"input_size": (112, 112), "window_size": 7,
+                                                                              "nb_blocks": (2, 2), "nb_heads": (3, 6)})])
+def test_swin_fp32_parity(name, overrides):
+    _, _, _, out, ref = _run(name, "swin", "fp32", 2, overrides)
+    rel, ab = _nerr(out, ref)
+    print(f"{name} fp32: normalised {rel:.3e} abs {ab:.3e}")
+    assert out.shape == ref.shape
+    assert rel < FP32_TOL
+
+
+@pytest.mark.parametrize("name", ["swin_tiny_patch4_window7_224", "swin_base_patch4_window7_224"])
+def test_swin_bf16_parity(name):
+    _, _, _, out, ref = _run(name, "swin", "bf16", 2)
+    rel, ab = _nerr(out, ref)
+    print(f"{name} bf16: normalised {rel:.3e} abs {ab:.3e}")
+    assert rel < BF16_TOL
+
+
+def test_swin_return_features():
+    import tfimm
+    from oracle import params
+    from oracle import swin as osw
+
+    model = tfimm.create_model("swin_tiny_patch4_window7_224", precision="fp32", device="cuda")
+    w = params.random_params(osw.param_shapes(model.cfg), seed=5)
+    model.load_weights_dict(w)
+    x = params.test_images(1, 224, 224)
+    y = model(x.cuda())
+    y2, feats = model(x.cuda(), return_features=True)
+    assert (y - y2).abs().max().item() < 1e-5
+    _, ofeats = osw.forward(model.cfg, w, x, return_features=True)
+    assert list(feats.keys()) == list(ofeats.keys()) == model.feature_names
+    for k in ("patch_embedding", "block_1", "stage_0", "block_7", "features_all", "features", "logits"):
+        assert _nerr(feats[k], ofeats[k])[0] < 5e-5, k
