@@ -49,7 +49,8 @@ const char* tfimm_b200_last_error(void);
 /* Number of SMs of the current device (0 if no device); used by the host to size workspaces. */
 int tfimm_b200_sm_count(void);
 
-/* Dense / 1x1 conv with fused epilogue:  C = residual + gamma * act(A @ W^T + bias).
+/* Dense / 1x1 conv with fused epilogue:  C = residual + gamma * act(A @ W^T + bias), or with
+ * act_after_residual != 0:  C = act(residual + gamma * (A @ W^T + bias))  (ResNet blocks, resnet.py:186-188).
  * A:[M,K] bf16 (ld = lda), W:[N,K] bf16 (ld = ldw), C/residual:[M,N] of out_dtype (bf16|f32);
  * residual may alias C (in-place residual stream).  tcgen05 tensor cores, TMA, fp32 accumulate.
  * Replaces tf.keras.layers.Dense at tfimm/architectures/vit.py:142-146, swin.py:124-128,343-345,
@@ -59,12 +60,12 @@ int tfimm_b200_sm_count(void);
  * force_block_n: 0 = auto, else 64/128/256 (testing). */
 int tfimm_b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias,
                          const float* gamma, const void* residual, int ldr, void* C, int ldc, int M, int N,
-                         int K, int act, int out_dtype, int force_block_n, void* stream);
+                         int K, int act, int act_after_residual, int out_dtype, int force_block_n, void* stream);
 
 /* Same contract in fp32 on CUDA cores (precision="fp32" parity mode). */
 int tfimm_b200_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
                         const float* gamma, const float* residual, int ldr, float* C, int ldc, int M, int N,
-                        int K, int act, void* stream);
+                        int K, int act, int act_after_residual, void* stream);
 
 /* LayerNorm over the last axis, fp32 statistics (tfimm/layers/factory.py:37-45).
  * in_stride/out_stride in elements (lets the caller normalise only token 0 of each image:
@@ -156,10 +157,23 @@ int tfimm_b200_se_gate(const float* pooled_sum, float inv_hw, const float* w_red
 int tfimm_b200_scale_channels(void* x, int dtype, const float* gate, int B, int HW, int C, void* stream);
 
 /* Window pooling on NHWC: mode 0 = max (ResNet stem MaxPool2D after ZeroPadding2D, resnet.py:536-539;
- * padding is explicit and never wins), mode 1 = average over in-bounds cells (AveragePooling2D
- * padding="same", resnet.py:299-301). */
+ * mode 2 = max where out-of-bounds cells are explicit zeros, i.e. ZeroPadding2D + VALID MaxPool2D),
+ * mode 1 = average over in-bounds cells (AveragePooling2D padding="same", resnet.py:299-301). */
 int tfimm_b200_pool2d(const void* x, int dtype, void* out, int B, int H, int W, int C, int ks, int stride,
                       int pad_t, int pad_l, int Ho, int Wo, int mode, void* stream);
+
+/* Grouped k x k convolution + folded-BN bias + activation (ResNeXt bottleneck conv2, resnet.py:230-238).
+ * cg = channels per group (in == out, one of 4/8/16/32); wgt: fp32 [k*k][cg][C] == TF kernel (kh,kw,cg,C). */
+int tfimm_b200_grouped_conv(const void* x, int dtype, const float* wgt, const float* bias, void* out, int B,
+                            int H, int W, int C, int cg, int ks, int stride, int pad, int Ho, int Wo, int act,
+                            void* stream);
+
+/* EcaModule gate: sigmoid(Conv1D_k(mean) over the channel axis, zero padded); layers/attention.py:120-130. */
+int tfimm_b200_eca_gate(const float* mean, const float* w, float* gate, int B, int C, int ks, void* stream);
+
+/* x = act(x * gate[b] + shortcut) in place: tail of SE / ECA residual blocks (resnet.py:182-188, 284-291). */
+int tfimm_b200_scale_add_act(void* x, int dtype, const float* gate, const void* shortcut, int B, int HW, int C,
+                             int act, void* stream);
 
 /* Elementwise dtype conversion. */
 int tfimm_b200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream);

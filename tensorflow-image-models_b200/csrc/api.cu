@@ -40,9 +40,9 @@ int sm_count() {
 
 // implemented in the other translation units
 int gemm_bf16_dispatch(const void*, int, const void*, int, const float*, const float*, const void*, int, void*,
-                       int, int, int, int, int, int, int, cudaStream_t);
+                       int, int, int, int, int, int, int, int, cudaStream_t);
 int gemm_f32(const float*, int, const float*, int, const float*, const float*, const float*, int, float*, int,
-             int, int, int, int, cudaStream_t);
+             int, int, int, int, int, cudaStream_t);
 int layernorm_rows(const void*, int, long, const float*, const float*, void*, int, long, long, int, float,
                    cudaStream_t);
 int layernorm_patch2x2(const void*, int, const float*, const float*, void*, int, int, int, int, int, float,
@@ -69,6 +69,10 @@ int se_gate(const float*, float, const float*, const float*, const float*, const
             int, int, cudaStream_t);
 int scale_channels(void*, int, const float*, int, int, int, cudaStream_t);
 int pool2d(const void*, int, void*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int grouped_conv(const void*, int, const float*, const float*, void*, int, int, int, int, int, int, int, int, int,
+                 int, int, cudaStream_t);
+int eca_gate(const float*, const float*, float*, int, int, int, cudaStream_t);
+int scale_add_act(void*, int, const float*, const void*, int, int, int, int, cudaStream_t);
 
 }  // namespace tfimm
 
@@ -83,15 +87,16 @@ int tfimm_b200_sm_count(void) { return tfimm::sm_count(); }
 
 int tfimm_b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
                          const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act,
-                         int out_dtype, int force_block_n, void* stream) {
-  return tfimm::gemm_bf16_dispatch(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act, out_dtype,
-                                   force_block_n, S(stream));
+                         int act_after_residual, int out_dtype, int force_block_n, void* stream) {
+  return tfimm::gemm_bf16_dispatch(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act,
+                                   act_after_residual, out_dtype, force_block_n, S(stream));
 }
 
 int tfimm_b200_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias, const float* gamma,
                         const float* residual, int ldr, float* C, int ldc, int M, int N, int K, int act,
-                        void* stream) {
-  return tfimm::gemm_f32(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act, S(stream));
+                        int act_after_residual, void* stream) {
+  return tfimm::gemm_f32(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act, act_after_residual,
+                         S(stream));
 }
 
 int tfimm_b200_layernorm(const void* x, int in_dtype, long in_stride, const float* gamma, const float* beta,
@@ -178,6 +183,21 @@ int tfimm_b200_scale_channels(void* x, int dtype, const float* gate, int B, int 
 int tfimm_b200_pool2d(const void* x, int dtype, void* out, int B, int H, int W, int C, int ks, int stride,
                       int pad_t, int pad_l, int Ho, int Wo, int mode, void* stream) {
   return tfimm::pool2d(x, dtype, out, B, H, W, C, ks, stride, pad_t, pad_l, Ho, Wo, mode, S(stream));
+}
+
+int tfimm_b200_grouped_conv(const void* x, int dtype, const float* wgt, const float* bias, void* out, int B,
+                            int H, int W, int C, int cg, int ks, int stride, int pad, int Ho, int Wo, int act,
+                            void* stream) {
+  return tfimm::grouped_conv(x, dtype, wgt, bias, out, B, H, W, C, cg, ks, stride, pad, Ho, Wo, act, S(stream));
+}
+
+int tfimm_b200_eca_gate(const float* mean, const float* w, float* gate, int B, int C, int ks, void* stream) {
+  return tfimm::eca_gate(mean, w, gate, B, C, ks, S(stream));
+}
+
+int tfimm_b200_scale_add_act(void* x, int dtype, const float* gate, const void* shortcut, int B, int HW, int C,
+                             int act, void* stream) {
+  return tfimm::scale_add_act(x, dtype, gate, shortcut, B, HW, C, act, S(stream));
 }
 
 }  // extern "C"

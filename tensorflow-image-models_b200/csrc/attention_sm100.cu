@@ -110,13 +110,19 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
         for (int j = 0; j < 32; ++j) cur[j] = r[j];
         if (c + 1 < nchunks) issue(c + 1, r);
+        if (c * 32 + 32 <= N) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < N) mx = fmaxf(mx, __uint_as_float(cur[j]));
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < N) mx = fmaxf(mx, __uint_as_float(cur[j]));
+        }
       }
     }
     const float moff = mx * scale_log2;
-    row_sum = 0.f;
+    const uint64_t sl2 = splat2(scale_log2), nmoff = splat2(-moff);
+    uint64_t sum2 = splat2(0.f);
     {
       uint32_t r[32], cur[32];
       issue(0, r);
@@ -126,13 +132,17 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int j = 0; j < 32; ++j) cur[j] = r[j];
         if (c + 1 < nchunks) issue(c + 1, r);
         uint32_t pk[16];
+        const bool full = (c * 32 + 32 <= N);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(cur[2 * j]), scale_log2, -moff));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(cur[2 * j + 1]), scale_log2, -moff));
-          const float p0 = (c * 32 + 2 * j < N) ? e0 : 0.f;
-          const float p1 = (c * 32 + 2 * j + 1 < N) ? e1 : 0.f;
-          row_sum += p0 + p1;
+          float t0, t1;
+          unpack2(fma2(pack2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), sl2, nmoff), t0, t1);
+          float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+          if (!full) {
+            p0 = (c * 32 + 2 * j < N) ? p0 : 0.f;
+            p1 = (c * 32 + 2 * j + 1 < N) ? p1 : 0.f;
+          }
+          sum2 = add2(sum2, pack2(p0, p1));
           pk[j] = pack_bf16x2(p0, p1);
         }
         // P chunk c overwrites score columns [16c, 16c+16): all already consumed (<= chunk c)
@@ -142,6 +152,11 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tmem_st_32x32b_x8(t_row + (uint32_t)(c * 16), lo);
         if (c < nfull) tmem_st_32x32b_x8(t_row + (uint32_t)(c * 16 + 8), hi);
       }
+    }
+    {
+      float s0, s1;
+      unpack2(sum2, s0, s1);
+      row_sum = s0 + s1;
     }
     tmem_st_wait();
   }
@@ -186,7 +201,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     if (lane == 0) {
       tma_store_3d(&tmap_o, sQ + (uint32_t)warp * 4096u, h * kDH, m0 + warp * 32, b);
       tma_store_commit();
-      tma_store_wait_all<0>();
+      tma_store_wait_read<0>();  // smem may be released; the global writes complete with the grid
     }
   }
   tcgen05_fence_before();

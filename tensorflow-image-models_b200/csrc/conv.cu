@@ -347,7 +347,8 @@ __global__ void scale_channels_kernel(T* __restrict__ x, const float* __restrict
 // ----------------------------------------------------------------------------------------------
 // spatial pooling windows (ResNet stem max-pool, "avg-down" shortcuts)
 // ----------------------------------------------------------------------------------------------
-// mode 0: max (padding acts as -inf), mode 1: average over the in-bounds cells only (TF "same").
+// mode 0: max (padding acts as -inf), mode 1: average over the in-bounds cells only (TF "same"),
+// mode 2: max where out-of-bounds cells are explicit zeros (ZeroPadding2D followed by a VALID MaxPool2D).
 template <typename T>
 __global__ void pool2d_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int Ho,
                               int Wo, int ks, int stride, int pad_t, int pad_l, int mode) {
@@ -363,7 +364,7 @@ __global__ void pool2d_kernel(const T* __restrict__ x, T* __restrict__ out, int 
     const long b = t / Ho;
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = mode == 0 ? -INFINITY : 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = mode == 1 ? 0.f : -INFINITY;
     int cnt = 0;
     for (int ky = 0; ky < ks; ++ky) {
       const int iy = oy * stride + ky - pad_t;
@@ -375,8 +376,12 @@ __global__ void pool2d_kernel(const T* __restrict__ x, T* __restrict__ out, int 
         ld8(x + ((b * H + iy) * W + ix) * (long)C + ch * 8, v);
         ++cnt;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = mode == 0 ? fmaxf(acc[j], v[j]) : acc[j] + v[j];
+        for (int j = 0; j < 8; ++j) acc[j] = mode == 1 ? acc[j] + v[j] : fmaxf(acc[j], v[j]);
       }
+    }
+    if (mode == 2 && cnt < ks * ks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
     }
     if (mode == 1) {
       const float inv = 1.0f / (float)max(cnt, 1);
@@ -447,7 +452,7 @@ int scale_channels(void* x, int dtype, const float* gate, int B, int HW, int C, 
 int pool2d(const void* x, int dtype, void* out, int B, int H, int W, int C, int ks, int stride, int pad_t,
            int pad_l, int Ho, int Wo, int mode, cudaStream_t stream) {
   TFIMM_CHECK_ARG(B > 0 && C % 8 == 0 && ks > 0 && stride > 0, "pool2d: need C%%8==0 (C=%d)", C);
-  TFIMM_CHECK_ARG(mode == 0 || mode == 1, "pool2d: mode must be 0 (max) or 1 (avg)");
+  TFIMM_CHECK_ARG(mode >= 0 && mode <= 2, "pool2d: mode must be 0 (max), 1 (avg) or 2 (zero-padded max)");
   const long total = (long)B * Ho * Wo * (C / 8);
   const unsigned grid = conv_grid_for(total, 256);
   if (dtype == kBF16)

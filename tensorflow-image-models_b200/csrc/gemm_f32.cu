@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                 const float* __restrict__ bias, const float* __restrict__ gamma,
                 const float* __restrict__ residual, int ldr, float* __restrict__ C, int ldc, int M, int N,
-                int K, int act) {
+                int K, int act, int act_post) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Ws[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -53,9 +53,10 @@ gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
       if (n >= N) continue;
       float v = acc[i][j];
       if (bias != nullptr) v += bias[n];
-      v = apply_act<true>(v, act);
+      if (!act_post) v = apply_act<true>(v, act);
       if (gamma != nullptr) v *= gamma[n];
       if (residual != nullptr) v += residual[(long)m * ldr + n];
+      if (act_post) v = apply_act<true>(v, act);
       C[(long)m * ldc + n] = v;
     }
   }
@@ -64,14 +65,14 @@ gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
 }  // namespace
 
 int gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias, const float* gamma,
-             const float* residual, int ldr, float* C, int ldc, int M, int N, int K, int act,
+             const float* residual, int ldr, float* C, int ldc, int M, int N, int K, int act, int act_post,
              cudaStream_t stream) {
   TFIMM_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_f32: M, N, K must be positive");
   TFIMM_CHECK_ARG(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0, "gemm_f32: K, lda, ldw must be multiples of 4");
   TFIMM_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(W) & 15u) == 0,
                   "gemm_f32: A and W must be 16-byte aligned");
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
-  gemm_f32_kernel<<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act);
+  gemm_f32_kernel<<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act, act_post);
   TFIMM_LAUNCH_OK("gemm_f32_kernel");
   return kOk;
 }

@@ -50,6 +50,7 @@ struct GemmParams {
   const float* gamma;  // [N] or null
   int act;
   int has_res;
+  int act_post;  // 1: activation applied after the residual add (ResNet: act(x + shortcut))
 };
 
 // v[j] (+ or *)= vec[n0 + j] on packed pairs; full chunks use 16-byte loads.
@@ -264,7 +265,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
         if (p.bias != nullptr) apply_vec<CH, false>(v, p.bias, n0, p.N);
-        apply_act_pairs(v, p.act);
+        if (!p.act_post) apply_act_pairs(v, p.act);
         if (p.gamma != nullptr) apply_vec<CH, true>(v, p.gamma, n0, p.N);
         if (p.has_res) {
           mbar_wait(res_bar(ew), cc & 1u);
@@ -284,6 +285,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         }
+        if (p.act_post) apply_act_pairs(v, p.act);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint4 u;
@@ -332,7 +334,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // ------------------------------ host side -----------------------------------
 template <int BLOCK_N, typename OutT>
 int launch_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
-                const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act,
+                const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act, int act_post,
                 cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int out_dtype = sizeof(OutT) == 2 ? kBF16 : kF32;
@@ -353,7 +355,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, const float* bia
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  GemmParams p{M, N, K, bias, gamma, act, residual != nullptr ? 1 : 0};
+  GemmParams p{M, N, K, bias, gamma, act, residual != nullptr ? 1 : 0, act_post};
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kernel<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, p);
@@ -381,7 +383,8 @@ int pick_block_n(int M, int N) {
 
 int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const float* bias,
                        const float* gamma, const void* residual, int ldr, void* C, int ldc, int M,
-                       int N, int K, int act, int out_dtype, int force_block_n, cudaStream_t stream) {
+                       int N, int K, int act, int act_post, int out_dtype, int force_block_n,
+                       cudaStream_t stream) {
   TFIMM_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: M, N, K must be positive (got %d %d %d)", M, N, K);
   TFIMM_CHECK_ARG(out_dtype == kBF16 || out_dtype == kF32, "gemm: out_dtype must be bf16 or f32");
   TFIMM_CHECK_ARG(K % 8 == 0, "gemm: K must be a multiple of 8 (got %d)", K);
@@ -392,9 +395,9 @@ int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const flo
   case BN:                                                                                            \
     return out_dtype == kBF16                                                                         \
                ? launch_gemm<BN, __nv_bfloat16>(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, \
-                                                N, K, act, stream)                                    \
+                                                N, K, act, act_post, stream)                          \
                : launch_gemm<BN, float>(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K,   \
-                                        act, stream);
+                                        act, act_post, stream);
   switch (bn) {
     TFIMM_GEMM_CASE(256)
     TFIMM_GEMM_CASE(128)

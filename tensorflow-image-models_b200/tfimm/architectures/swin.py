@@ -187,6 +187,8 @@ class SwinTransformer(Model):
 
     def _build(self):
         super()._build()
+        if self.device.type == "meta":
+            return
         c = self.cfg
         index = torch.from_numpy(relative_position_index(c.window_size))
         for i, (h, w, dim, heads, blocks) in enumerate(self._stage_geometry()):

@@ -27,8 +27,8 @@ _F = _c.c_float
 
 # name -> argtypes; restype is int (status) unless listed in _SPECIAL
 SIGNATURES = {
-    "tfimm_b200_gemm_bf16": [_P, _I, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "tfimm_b200_gemm_f32": [_P, _I, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
+    "tfimm_b200_gemm_bf16": [_P, _I, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "tfimm_b200_gemm_f32": [_P, _I, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "tfimm_b200_layernorm": [_P, _I, _L, _P, _P, _P, _I, _L, _L, _I, _F, _P],
     "tfimm_b200_layernorm_patch2x2": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "tfimm_b200_patch_merge_ln": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
@@ -45,6 +45,9 @@ SIGNATURES = {
     "tfimm_b200_se_gate": [_P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "tfimm_b200_scale_channels": [_P, _I, _P, _I, _I, _I, _P],
     "tfimm_b200_pool2d": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "tfimm_b200_grouped_conv": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "tfimm_b200_eca_gate": [_P, _P, _P, _I, _I, _I, _P],
+    "tfimm_b200_scale_add_act": [_P, _I, _P, _P, _I, _I, _I, _I, _P],
 }
 _SPECIAL = {
     "tfimm_b200_version": ([], _c.c_char_p),

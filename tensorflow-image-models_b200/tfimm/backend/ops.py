@@ -70,8 +70,10 @@ def act_code(act) -> int:
         raise ValueError(f"Unknown activation: {act}.")
 
 
-def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dtype=None, block_n=0):
-    """out = residual + gamma * act(a @ w.T + bias).  a:(M,K), w:(N,K); bf16 -> tcgen05, fp32 -> SIMT."""
+def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dtype=None, block_n=0,
+         act_after_residual=False):
+    """out = residual + gamma * act(a @ w.T + bias)  (act_after_residual: act(residual + gamma*(...))).
+    a:(M,K), w:(N,K); bf16 -> tcgen05, fp32 -> SIMT."""
     _cuda(a, w, bias, gamma, residual, out)
     M, K = a.shape
     N = w.shape[0]
@@ -90,13 +92,13 @@ def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dty
         assert w.dtype == torch.bfloat16
         _call("tfimm_b200_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
               _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
-              _code(out), block_n, _stream(), flops=2.0 * M * N * K,
+              int(bool(act_after_residual)), _code(out), block_n, _stream(), flops=2.0 * M * N * K,
               nbytes=_nbytes(a, w, out, residual))
     else:
         assert a.dtype == torch.float32 and w.dtype == torch.float32 and out.dtype == torch.float32
         _call("tfimm_b200_gemm_f32", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
               _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
-              _stream(), flops=2.0 * M * N * K, nbytes=_nbytes(a, w, out, residual))
+              int(bool(act_after_residual)), _stream(), flops=2.0 * M * N * K, nbytes=_nbytes(a, w, out, residual))
     return out
 
 
@@ -317,5 +319,39 @@ def pool2d(x, ks, stride, padding, mode):
     Ho, Wo, pt, pl = conv_geometry(H, W, ks, stride, padding)
     out = torch.empty((B, Ho, Wo, C), device=x.device, dtype=x.dtype)
     _call("tfimm_b200_pool2d", x.data_ptr(), _code(x), out.data_ptr(), B, H, W, C, ks, stride, pt, pl, Ho, Wo,
-          0 if mode == "max" else 1, _stream(), nbytes=_nbytes(x, out))
+          {"max": 0, "avg": 1, "max_zero_pad": 2}[mode], _stream(), nbytes=_nbytes(x, out))
     return out
+
+
+def grouped_conv(x, wgt, bias, cg, ks, stride, pad, act=None):
+    """Grouped k x k conv (cg channels per group, in == out) + bias + act.  wgt: (ks*ks, cg, C) fp32."""
+    _cuda(x, wgt, bias)
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    Ho, Wo, _, _ = conv_geometry(H, W, ks, stride, pad)
+    out = torch.empty((B, Ho, Wo, C), device=x.device, dtype=x.dtype)
+    _call("tfimm_b200_grouped_conv", x.data_ptr(), _code(x), wgt.data_ptr(), _ptr(bias), out.data_ptr(), B, H, W, C,
+          cg, ks, stride, pad, Ho, Wo, act_code(act), _stream(), flops=2.0 * B * Ho * Wo * C * cg * ks * ks,
+          nbytes=_nbytes(x, out))
+    return out
+
+
+def eca_gate(mean, w):
+    """mean: (B, C) fp32, w: (ks,) fp32 -> gate (B, C) fp32."""
+    _cuda(mean, w)
+    B, C = mean.shape
+    gate = torch.empty_like(mean)
+    _call("tfimm_b200_eca_gate", mean.data_ptr(), w.data_ptr(), gate.data_ptr(), B, C, w.numel(), _stream(),
+          nbytes=_nbytes(mean, gate))
+    return gate
+
+
+def scale_add_act_(x, gate, shortcut, act):
+    """In place: x = act(x * gate[b] + shortcut)."""
+    _cuda(x, gate, shortcut)
+    assert x.is_contiguous() and shortcut.is_contiguous() and x.shape == shortcut.shape and x.dtype == shortcut.dtype
+    B, C = gate.shape
+    HW = x.numel() // (B * C)
+    _call("tfimm_b200_scale_add_act", x.data_ptr(), _code(x), gate.data_ptr(), shortcut.data_ptr(), B, HW, C,
+          act_code(act), _stream(), nbytes=3 * _nbytes(x))
+    return x

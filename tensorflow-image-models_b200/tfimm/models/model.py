@@ -120,7 +120,10 @@ class Model:
     def _build(self):
         gen = torch.Generator().manual_seed(self._seed)
         for key, spec in self.param_specs().items():
-            self.params[key] = _init_tensor(spec, gen).to(self.device)
+            if self.device.type == "meta":  # shapes only (used to enumerate variables cheaply)
+                self.params[key] = torch.empty(tuple(spec.shape), device="meta")
+            else:
+                self.params[key] = _init_tensor(spec, gen).to(self.device)
         self._plan = None
 
     @property

@@ -33,6 +33,16 @@ def pytest_collection_modifyitems(config, items):
 
 
 @pytest.fixture(scope="session", autouse=True)
+def _exact_fp32_references():
+    """The fp32 PyTorch references the kernels are compared with must not silently use TF32."""
+    import torch
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+@pytest.fixture(scope="session", autouse=True)
 def _built_library():
     lib = PKG / "tfimm" / "backend" / "libtfimm_b200.so"
     if not lib.exists():

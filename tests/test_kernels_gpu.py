@@ -360,3 +360,100 @@ def test_window_attention_bf16(h, w, ws, shift, H):
     out32 = ops.attention(qkv.float(), B * nw, n, H, dh, dh ** -0.5, bias=bias, mask=mask, row_map=rm, nw_img=nw)
     torch.cuda.synchronize()
     assert (out32 - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("ks,stride,padding,C", [(3, 2, "same", 3), (3, 1, 1, 16), (7, 2, 3, 3), (1, 2, 0, 64), (3, 2, "symmetric", 24)])
+def test_im2col_gemm_equals_conv(ks, stride, padding, C):
+    ops = _ops()
+    B, H, W, Cout = 2, 21, 18, 40
+    g = torch.Generator(device="cuda").manual_seed(ks * 7 + C)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g)
+    w = torch.randn(ks, ks, C, Cout, device="cuda", generator=g) / (ks * C ** 0.5)
+    cols, Ho, Wo = ops.im2col(x, ks, stride, padding, torch.float32)
+    K = ks * ks * C
+    w2 = torch.zeros(Cout, cols.shape[1], device="cuda")
+    w2[:, :K] = w.reshape(K, Cout).t()
+    out = ops.gemm(cols, w2.contiguous()).view(B, Ho, Wo, Cout)
+    torch.cuda.synchronize()
+    _, _, pt, pl = ops.conv_geometry(H, W, ks, stride, padding)
+    tot_h, tot_w = max((Ho - 1) * stride + ks - H, 0), max((Wo - 1) * stride + ks - W, 0)
+    xin = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (pl, max(tot_w - pl, 0), pt, max(tot_h - pt, 0)))
+    ref = torch.nn.functional.conv2d(xin, w.permute(3, 2, 0, 1), stride=stride).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() < 1e-4
+
+
+def test_se_gate_scale_and_eca():
+    ops = _ops()
+    B, H, W, C, rd = 3, 5, 7, 48, 6
+    g = torch.Generator(device="cuda").manual_seed(33)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g)
+    wr = torch.randn(rd, C, device="cuda", generator=g) / C ** 0.5
+    br = torch.randn(rd, device="cuda", generator=g)
+    we = torch.randn(C, rd, device="cuda", generator=g) / rd ** 0.5
+    be = torch.randn(C, device="cuda", generator=g)
+    pooled_sum = x.sum(dim=(1, 2)).contiguous()
+    gate = ops.se_gate(pooled_sum, H * W, wr, br, we, be, act="swish")
+    torch.cuda.synchronize()
+    m = x.mean(dim=(1, 2))
+    hdn = m @ wr.t() + br
+    ref = torch.sigmoid((hdn * torch.sigmoid(hdn)) @ we.t() + be)
+    assert (gate - ref).abs().max().item() < 1e-5
+    y = x.clone()
+    ops.scale_channels_(y, gate)
+    assert (y - x * ref[:, None, None, :]).abs().max().item() < 1e-5
+    wk = torch.randn(5, device="cuda", generator=g)
+    eg = ops.eca_gate(m.contiguous(), wk)
+    eref = torch.sigmoid(torch.nn.functional.conv1d(torch.nn.functional.pad(m, (2, 2))[:, None], wk[None, None])[:, 0])
+    assert (eg - eref).abs().max().item() < 1e-5
+    sc = torch.randn(B, H, W, C, device="cuda", generator=g)
+    z = x.clone()
+    ops.scale_add_act_(z, ref.contiguous(), sc, "relu")
+    torch.cuda.synchronize()
+    assert (z - torch.relu(x * ref[:, None, None, :] + sc)).abs().max().item() < 1e-5
+
+
+def test_pool2d_modes():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(34)
+    x = torch.randn(2, 9, 11, 16, device="cuda", generator=g) - 1.0  # mostly negative: zero padding matters
+    out = ops.pool2d(x, 3, 2, 1, "max_zero_pad")
+    ref = torch.nn.functional.max_pool2d(torch.nn.functional.pad(x.permute(0, 3, 1, 2), (1, 1, 1, 1)), 3, 2).permute(0, 2, 3, 1)
+    assert (out - ref).abs().max().item() == 0
+    out = ops.pool2d(x, 2, 2, "same", "avg")
+    xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ones = torch.nn.functional.pad(torch.ones_like(x.permute(0, 3, 1, 2)), (0, 1, 0, 1))
+    ref = (torch.nn.functional.avg_pool2d(xp, 2, 2) / torch.nn.functional.avg_pool2d(ones, 2, 2)).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("cg,stride", [(4, 1), (8, 2), (16, 1), (32, 2)])
+def test_grouped_conv(cg, stride):
+    ops = _ops()
+    B, H, W, groups = 2, 10, 9, 4
+    C = cg * groups
+    g = torch.Generator(device="cuda").manual_seed(cg)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g)
+    w = torch.randn(3, 3, cg, C, device="cuda", generator=g) / (3 * cg ** 0.5)
+    bias = torch.randn(C, device="cuda", generator=g)
+    out = ops.grouped_conv(x, w.reshape(9, cg, C).contiguous(), bias, cg, 3, stride, 1, act="relu")
+    torch.cuda.synchronize()
+    ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, stride=stride,
+                                                padding=1, groups=groups)).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() < 1e-4
+
+
+def test_gemm_act_after_residual():
+    ops = _ops()
+    M, N, K = 300, 136, 72
+    g = torch.Generator(device="cuda").manual_seed(35)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    out = ops.gemm(a, w, bias=bias, act="relu", residual=res, act_after_residual=True)
+    torch.cuda.synchronize()
+    ref = torch.relu(a.float() @ w.float().t() + bias + res.float())
+    assert (out.float() - ref).abs().max().item() < 2e-2 + 4e-3 * ref.abs().max().item()

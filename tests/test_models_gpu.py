@@ -189,3 +189,75 @@ def test_swin_return_features():
     assert list(feats.keys()) == list(ofeats.keys()) == model.feature_names
     for k in ("patch_embedding", "block_1", "stage_0", "block_7", "features_all", "features", "logits"):
         assert _nerr(feats[k], ofeats[k])[0] < 5e-5, k
+
+
+@pytest.mark.parametrize("name,overrides", [
+    ("efficientnet_b0", {}),                                   # TF "same" padding, BN eps 1e-3, SE, swish
+    ("pt_efficientnet_b0", {"input_size": (192, 160)}),        # symmetric padding
+    ("mobilenet_v2_100", {}),                                  # relu6, no SE
+    ("efficientnet_es", {}),                                   # EdgeResidual blocks
+    ("efficientnet_lite0", {}),
+    ("efficientnet_v2_b0", {"input_size": (128, 128)}),        # cn + er + ir mix
+])
+def test_efficientnet_fp32_parity(name, overrides):
+    _, _, _, out, ref = _run(name, "efficientnet", "fp32", 2, overrides)
+    rel, ab = _nerr(out, ref)
+    print(f"{name} fp32: normalised {rel:.3e} abs {ab:.3e}")
+    assert out.shape == ref.shape
+    assert rel < FP32_TOL
+
+
+@pytest.mark.parametrize("name,size", [("efficientnet_b0", 224), ("efficientnet_b4", 380)])
+def test_efficientnet_bf16_parity(name, size):
+    _, _, _, out, ref = _run(name, "efficientnet", "bf16", 2, {"input_size": (size, size)})
+    rel, ab = _nerr(out, ref)
+    print(f"{name} bf16: normalised {rel:.3e} abs {ab:.3e}")
+    assert rel < 3e-2  # bf16 activation stream through 16-32 BN-folded blocks
+
+
+@pytest.mark.parametrize("name", ["resnet18", "resnet50", "resnet50d", "resnext50_32x4d", "seresnet50", "ecaresnet26t",
+                                  "resnetrs50"])
+def test_resnet_fp32_parity(name):
+    _, _, _, out, ref = _run(name, "resnet", "fp32", 2, {"input_size": (128, 128)})
+    rel, ab = _nerr(out, ref)
+    print(f"{name} fp32: normalised {rel:.3e} abs {ab:.3e}")
+    assert out.shape == ref.shape
+    assert rel < FP32_TOL
+
+
+@pytest.mark.parametrize("name", ["resnet50", "resnext50_32x4d"])
+def test_resnet_bf16_parity(name):
+    _, _, _, out, ref = _run(name, "resnet", "bf16", 2)
+    rel, ab = _nerr(out, ref)
+    print(f"{name} bf16: normalised {rel:.3e} abs {ab:.3e}")
+    assert rel < 3e-2
+
+
+def _golden_cases():
+    from pathlib import Path
+
+    return sorted(p.name for p in (Path(__file__).resolve().parent / "golden").glob("*.npz"))
+
+
+@pytest.mark.parametrize("fixture", _golden_cases())
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_engine_matches_committed_golden_logits(fixture, precision):
+    """Engine vs the stored oracle logits (tests/golden, tools/make_golden.py): nothing here reads the
+    oracle's code path, only the committed numbers."""
+    import importlib
+    from pathlib import Path
+
+    import numpy as np
+
+    import tfimm
+    from oracle import params
+
+    data = np.load(Path(__file__).resolve().parent / "golden" / fixture, allow_pickle=True)
+    meta = data["meta"].item()
+    mod = importlib.import_module(f"oracle.{meta['family']}")
+    model = tfimm.create_model(meta["model"], precision=precision, device="cuda", **meta["overrides"])
+    model.load_weights_dict(params.random_params(mod.param_shapes(model.cfg), seed=meta["seed"]))
+    out = model(torch.from_numpy(data["images"]).cuda())
+    rel, ab = _nerr(out, torch.from_numpy(data["logits"]))
+    print(f"{fixture} {precision}: normalised {rel:.3e} abs {ab:.3e}")
+    assert rel < (FP32_TOL if precision == "fp32" else 3e-2)
