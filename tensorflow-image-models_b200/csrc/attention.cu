@@ -271,6 +271,7 @@ __global__ void attention_f32_kernel(const float* __restrict__ qkv, float* __res
 }  // namespace
 
 int attention_bf16_tc(const void* qkv, void* out, int B, int N, int H, float scale, cudaStream_t stream);
+int attention_bf16_tc2(const void* qkv, void* out, int B, int N, int H, float scale, cudaStream_t stream);
 
 int attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, float scale,
                    cudaStream_t stream) {
@@ -283,11 +284,15 @@ int attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, floa
                   "attention: pointers must be 16-byte aligned");
   // Short sequences (ViT-B/16 @224: N = 197) run on tcgen05; longer ones on the resident-KV mma.sync
   // kernel.  TFIMM_B200_ATTN=mma forces the latter (debugging aid).
-  static const bool force_mma = [] {
+  // TFIMM_B200_ATTN = "mma" (legacy mma.sync) | "tc1" (one CTA per 128-query tile) | default: persistent tc2.
+  static const int mode = [] {
     const char* e = getenv("TFIMM_B200_ATTN");
-    return e != nullptr && e[0] == 'm';
+    if (e == nullptr) return 2;
+    if (e[0] == 'm') return 0;
+    return (e[0] == 't' && e[1] == 'c' && e[2] == '1') ? 1 : 2;
   }();
-  if (N <= 256 && !force_mma) return attention_bf16_tc(qkv, out, B, N, H, scale, stream);
+  if (N <= 256 && mode == 2) return attention_bf16_tc2(qkv, out, B, N, H, scale, stream);
+  if (N <= 256 && mode == 1) return attention_bf16_tc(qkv, out, B, N, H, scale, stream);
   auto q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   auto o = reinterpret_cast<__nv_bfloat16*>(out);
   if (N <= 128) return launch_vit_attention<4, 2>(q, o, B, N, H, scale, stream);

@@ -212,7 +212,295 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// v2: persistent, warp-specialised, two-stage pipeline (one CTA per SM)
+// ---------------------------------------------------------------------------------------------------
+//   warp 0      TMA producer: Q (256 rows), K, V of work item i+1 while item i is being processed
+//   warp 1      tcgen05.mma issuer: S = Q K^T for both 128-query tiles, later O = P V for both
+//   warps 2..5  softmax / epilogue group A (queries 0..127,   TMEM columns   0..255)
+//   warps 6..9  softmax / epilogue group B (queries 128..255, TMEM columns 256..511)
+// A work item is one (image, head).  Per 128-query tile the TMEM region holds S (fp32, cols [0,npad)), then P
+// (bf16 packed, cols [0,npad/2)) written over the consumed scores, then O (cols [128,192)).
+constexpr int kP2Threads = 320;
+constexpr int kP2QBytes = 256 * 128;
+constexpr int kP2StageBytes = kP2QBytes + 2 * kKVBytesMax;  // 96 KB
+constexpr int kP2SmemBytes = 2 * kP2StageBytes + 256 + 1024;
+
+__global__ void __launch_bounds__(kP2Threads, 1)
+vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                         const __grid_constant__ CUtensorMap tmap_o, int N, int H, int total_items,
+                         float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + 2 * kP2StageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (2 + s); };
+  auto sfull_bar = [&](int r) { return bars + 8u * (4 + r); };
+  auto pready_bar = [&](int r) { return bars + 8u * (6 + r); };
+  auto ofull_bar = [&](int r) { return bars + 8u * (8 + r); };
+  auto tempty_bar = [&](int r) { return bars + 8u * (10 + r); };
+  const uint32_t tmem_ptr_smem = bars + 8u * 12;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * kDH;
+  const int npad = (N + 15) & ~15;
+  const int mtiles = N > kQRows ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_kv);
+    prefetch_tmap(&tmap_o);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 4 * mtiles);
+    }
+    for (int r = 0; r < 2; ++r) {
+      mbar_init(sfull_bar(r), 1);
+      mbar_init(pready_bar(r), 4);
+      mbar_init(ofull_bar(r), 1);
+      mbar_init(tempty_bar(r), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+  if (warp == 0) {
+    // ------------------------------------- TMA producer -------------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+        const int b = item / H, h = item % H;
+        const uint32_t sQ = smem_base + s * kP2StageBytes, sK = sQ + kP2QBytes, sV = sK + kKVBytesMax;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), (uint32_t)(kP2QBytes + 2 * npad * 128));
+        tma_load_3d(sQ, &tmap_q, full_bar(s), h * kDH, 0, b);
+        tma_load_3d(sK, &tmap_kv, full_bar(s), D + h * kDH, 0, b);
+        tma_load_3d(sV, &tmap_kv, full_bar(s), 2 * D + h * kDH, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------- MMA issuer --------------------------------------
+    const uint32_t idesc_s = umma_idesc_bf16_f32(kQRows, npad);
+    const uint32_t idesc_o = umma_idesc_bf16_f32(kQRows, kDH, /*b_mn_major=*/true);
+    const int ksteps = npad >> 4;
+    int it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (uint32_t)(it >> 1) & 1u, par = (uint32_t)it & 1u;
+      const uint32_t sQ = smem_base + s * kP2StageBytes, sK = sQ + kP2QBytes, sV = sK + kKVBytesMax;
+      mbar_wait(full_bar(s), ph);
+      for (int r = 0; r < mtiles; ++r) {
+        mbar_wait(tempty_bar(r), par ^ 1u);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint64_t dq = umma_desc_k_sw128(sQ + (uint32_t)r * (kQRows * 128)), dk = umma_desc_k_sw128(sK);
+#pragma unroll
+          for (int k = 0; k < kDH / 16; ++k)
+            umma_bf16_ss(tmem_base + (uint32_t)(r * 256), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s,
+                         (uint32_t)(k != 0));
+          umma_commit(sfull_bar(r));
+        }
+        __syncwarp();
+      }
+      for (int r = 0; r < mtiles; ++r) {
+        mbar_wait(pready_bar(r), par);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t t0 = tmem_base + (uint32_t)(r * 256);
+          for (int j = 0; j < ksteps; ++j) {
+            const uint64_t dv = umma_desc_mn_sw128(sV + (uint32_t)(j * 2048), (uint32_t)(npad * 128));
+            umma_bf16_ts(t0 + kOCol, t0 + (uint32_t)(j * 8), dv, idesc_o, (uint32_t)(j != 0));
+          }
+          umma_commit(ofull_bar(r));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------- softmax + epilogue groups -------------------------------
+    const int r = (warp - 2) >> 2;  // 0: queries 0..127, 1: queries 128..255
+    const int q = warp & 3;         // TMEM lane quarter
+    if (r < mtiles) {
+      const int row0 = r * kQRows + q * 32;  // first query row of this warp inside the image
+      const bool warp_has_rows = row0 < N;
+      const uint32_t t_row = tmem_base + (uint32_t)(r * 256) + ((uint32_t)(q * 32) << 16);
+      const int nfull = npad >> 5;
+      const bool tail16 = (npad & 16) != 0;
+      const int nchunks = nfull + (tail16 ? 1 : 0);
+      const uint64_t sl2 = splat2(scale_log2);
+      auto issue = [&](int c, uint32_t (&rg)[32]) {
+        if (c < nfull) {
+          tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), rg);
+        } else {
+          uint32_t t16[16];
+          tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 32), t16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rg[j] = t16[j];
+#pragma unroll
+          for (int j = 16; j < 32; ++j) rg[j] = 0xff800000u;
+        }
+      };
+      int it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t par = (uint32_t)it & 1u;
+        const int b = item / H, h = item % H;
+        mbar_wait(sfull_bar(r), par);
+        tcgen05_fence_after();
+        float row_sum = 1.f;
+        if (warp_has_rows) {
+          float mx = -INFINITY;
+          {
+            uint32_t rg[32], cur[32];
+            issue(0, rg);
+            for (int c = 0; c < nchunks; ++c) {
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) cur[j] = rg[j];
+              if (c + 1 < nchunks) issue(c + 1, rg);
+              if (c * 32 + 32 <= N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c * 32 + j < N) mx = fmaxf(mx, __uint_as_float(cur[j]));
+              }
+            }
+          }
+          const uint64_t nmoff = splat2(-mx * scale_log2);
+          uint64_t sum2 = splat2(0.f);
+          {
+            uint32_t rg[32], cur[32];
+            issue(0, rg);
+            for (int c = 0; c < nchunks; ++c) {
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) cur[j] = rg[j];
+              if (c + 1 < nchunks) issue(c + 1, rg);
+              uint32_t pk[16];
+              const bool full = (c * 32 + 32 <= N);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float t0, t1;
+                unpack2(fma2(pack2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), sl2, nmoff), t0, t1);
+                float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+                if (!full) {
+                  p0 = (c * 32 + 2 * j < N) ? p0 : 0.f;
+                  p1 = (c * 32 + 2 * j + 1 < N) ? p1 : 0.f;
+                }
+                sum2 = add2(sum2, pack2(p0, p1));
+                pk[j] = pack_bf16x2(p0, p1);
+              }
+              uint32_t lo[8], hi[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { lo[j] = pk[j]; hi[j] = pk[8 + j]; }
+              tmem_st_32x32b_x8(t_row + (uint32_t)(c * 16), lo);
+              if (c < nfull) tmem_st_32x32b_x8(t_row + (uint32_t)(c * 16 + 8), hi);
+            }
+          }
+          tmem_st_wait();
+          float s0, s1;
+          unpack2(sum2, s0, s1);
+          row_sum = s0 + s1;
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pready_bar(r));
+
+        mbar_wait(ofull_bar(r), par);
+        tcgen05_fence_after();
+        uint32_t o[64];
+        if (warp_has_rows) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t t32[32];
+            tmem_ld_32x32b_x32(t_row + kOCol + (uint32_t)(c * 32), t32);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[c * 32 + j] = t32[j];
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(r));  // the MMA warp may start the next item's S in this region
+        if (warp_has_rows) {
+          const float inv = 1.0f / row_sum;
+          const uint32_t slab = smem_base + s * kP2StageBytes + (uint32_t)row0 * 128u;  // this warp's dead Q rows
+          uint8_t* my_row = smem_gen + (slab - smem_base) + lane * 128;
+          const int sw = lane & 7;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_o, slab, h * kDH, row0, b);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));  // K/V/Q of this stage may be overwritten
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
+
+int attention_bf16_tc2(const void* qkv, void* out, int B, int N, int H, float scale, cudaStream_t stream) {
+  const int D = H * kDH;
+  const int npad = (N + 15) & ~15;
+  CUtensorMap tq, tkv, to;
+  {
+    const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)N, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)N * 3 * D * 2};
+    const uint32_t box_q[3] = {kDH, 256, 1};
+    const uint32_t box_kv[3] = {kDH, (uint32_t)npad, 1};
+    int st;
+    if ((st = make_tmap(&tq, qkv, kBF16, 3, dims, strides, box_q, "attention q")) != kOk) return st;
+    if ((st = make_tmap(&tkv, qkv, kBF16, 3, dims, strides, box_kv, "attention kv")) != kOk) return st;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)N, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)N * D * 2};
+    const uint32_t box[3] = {kDH, 32, 1};
+    int st;
+    if ((st = make_tmap(&to, out, kBF16, 3, dims, strides, box, "attention out")) != kOk) return st;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    TFIMM_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2SmemBytes));
+    attr_set = true;
+  }
+  const int items = B * H;
+  const int grid = items < sm_count() ? items : sm_count();
+  vit_attention_tc2_kernel<<<grid, kP2Threads, kP2SmemBytes, stream>>>(tq, tkv, to, N, H, items,
+                                                                       scale * 1.4426950408889634f);
+  TFIMM_LAUNCH_OK("vit_attention_tc2_kernel");
+  return kOk;
+}
 
 int attention_bf16_tc(const void* qkv, void* out, int B, int N, int H, float scale, cudaStream_t stream) {
   const int D = H * kDH;

@@ -14,7 +14,17 @@
 //                    efficientnet.py:256, swin.py:456, layers/classifier.py:34).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace tfimm {
+
+int dwconv_bias_act_pairs(const void* x, int dtype, const float* wgt, const float* bias, void* out, float* pool_sum,
+                          int B, int H, int W, int C, int ks, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                          int act, cudaStream_t stream);
+int dwconv7_ln_cluster(const void* x, int in_dtype, const float* wgt, const float* bias, const float* gamma,
+                       const float* beta, void* out, int out_dtype, int B, int H, int W, int C, float eps,
+                       cudaStream_t stream);
+
 namespace {
 
 // ----------------------------------------------------------------------------------------------
@@ -131,77 +141,77 @@ dwconv_ln_kernel(const InT* __restrict__ x, const float* __restrict__ wgt /*[KS*
 // ----------------------------------------------------------------------------------------------
 // generic depthwise conv + bias + activation (+ fused squeeze)
 // ----------------------------------------------------------------------------------------------
-// One thread: 4 channels x TW output pixels of one output row.  Threads of a warp cover 128
-// consecutive channels (coalesced 8-byte/16-byte accesses); warps tile (channel group, x strip, y, b).
+// One warp: one output row x 128 channels (4 per lane, coalesced 8/16-byte accesses).  The k*k taps of the
+// lane's channels live in registers for the whole row, the row is walked in strips of TW pixels with a sliding
+// input window, and the squeeze sums are accumulated in registers -> ONE atomic per (lane, channel) per row.
 template <typename T, int KS, int STRIDE, int TW>
 __global__ void __launch_bounds__(128)
 dwconv_act_kernel(const T* __restrict__ x, const float* __restrict__ wgt /*[KS*KS][C]*/,
                   const float* __restrict__ bias, T* __restrict__ out, float* __restrict__ pool_sum,
                   int B, int H, int W, int C, int Ho, int Wo, int pad_t, int pad_l, int act) {
   const int cgroups = (C + 127) >> 7;
-  const int segs = (Wo + TW - 1) / TW;
   const long unit = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
-  const long units = (long)B * Ho * segs * cgroups;
+  const long units = (long)B * Ho * cgroups;
   if (unit >= units) return;
   const int lane = threadIdx.x & 31;
   const int cg = (int)(unit % cgroups);
-  long t = unit / cgroups;
+  const long t = unit / cgroups;
   const int oy = (int)(t % Ho);
-  t /= Ho;
-  const int seg = (int)(t % segs);
-  const int b = (int)(t / segs);
+  const int b = (int)(t / Ho);
   const int c = cg * 128 + lane * 4;
   if (c >= C) return;
-  const int ox0 = seg * TW;
-  constexpr int IW = (TW - 1) * STRIDE + KS;  // input columns feeding the strip
-  float4 acc[TW];
+  constexpr int IW = (TW - 1) * STRIDE + KS;  // input columns feeding one strip
+  float4 wv[KS * KS];
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) wv[i] = ld4f(wgt + (size_t)i * C + c);
   const float4 bv = bias != nullptr ? ld4f(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < TW; ++i) acc[i] = bv;
+  float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-  for (int ky = 0; ky < KS; ++ky) {
-    const int iy = oy * STRIDE + ky - pad_t;
-    if (iy < 0 || iy >= H) continue;
-    float4 wv[KS];
+  for (int ox0 = 0; ox0 < Wo; ox0 += TW) {
+    float4 acc[TW];
 #pragma unroll
-    for (int kx = 0; kx < KS; ++kx) wv[kx] = ld4f(wgt + (size_t)(ky * KS + kx) * C + c);
-    const T* row = x + (((long)b * H + iy) * W) * C + c;
+    for (int i = 0; i < TW; ++i) acc[i] = bv;
 #pragma unroll
-    for (int ix = 0; ix < IW; ++ix) {
-      const int gx = ox0 * STRIDE + ix - pad_l;
-      if (gx < 0 || gx >= W) continue;
-      const float4 v = ld4f(row + (long)gx * C);
+    for (int ky = 0; ky < KS; ++ky) {
+      const int iy = oy * STRIDE + ky - pad_t;
+      if (iy < 0 || iy >= H) continue;
+      const T* row = x + (((long)b * H + iy) * W) * C + c;
 #pragma unroll
-      for (int kx = 0; kx < KS; ++kx) {
-        // ix = ox*STRIDE + kx
-        if ((ix - kx) >= 0 && (ix - kx) % STRIDE == 0 && (ix - kx) / STRIDE < TW) {
-          const int ox = (ix - kx) / STRIDE;
-          acc[ox].x = fmaf(v.x, wv[kx].x, acc[ox].x);
-          acc[ox].y = fmaf(v.y, wv[kx].y, acc[ox].y);
-          acc[ox].z = fmaf(v.z, wv[kx].z, acc[ox].z);
-          acc[ox].w = fmaf(v.w, wv[kx].w, acc[ox].w);
+      for (int ix = 0; ix < IW; ++ix) {
+        const int gx = ox0 * STRIDE + ix - pad_l;
+        if (gx < 0 || gx >= W) continue;
+        const float4 v = ld4f(row + (long)gx * C);
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          // ix = ox*STRIDE + kx
+          if ((ix - kx) >= 0 && (ix - kx) % STRIDE == 0 && (ix - kx) / STRIDE < TW) {
+            const int ox = (ix - kx) / STRIDE;
+            const float4 w4 = wv[ky * KS + kx];
+            acc[ox].x = fmaf(v.x, w4.x, acc[ox].x);
+            acc[ox].y = fmaf(v.y, w4.y, acc[ox].y);
+            acc[ox].z = fmaf(v.z, w4.z, acc[ox].z);
+            acc[ox].w = fmaf(v.w, w4.w, acc[ox].w);
+          }
         }
       }
     }
-  }
-  float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < TW; ++i) {
-    if (ox0 + i < Wo) {
-      float4 o;
-      o.x = apply_act<true>(acc[i].x, act);
-      o.y = apply_act<true>(acc[i].y, act);
-      o.z = apply_act<true>(acc[i].z, act);
-      o.w = apply_act<true>(acc[i].w, act);
-      // round first so the pooled statistics see exactly what the next layer reads
-      T* dst = out + (((long)b * Ho + oy) * Wo + ox0 + i) * C + c;
-      st4f(dst, o);
-      if (pool_sum != nullptr) {
-        if constexpr (sizeof(T) == 2) {
-          const float2 r0 = unpack_bf16x2(pack_bf16x2(o.x, o.y)), r1 = unpack_bf16x2(pack_bf16x2(o.z, o.w));
-          ps.x += r0.x; ps.y += r0.y; ps.z += r1.x; ps.w += r1.y;
-        } else {
-          ps.x += o.x; ps.y += o.y; ps.z += o.z; ps.w += o.w;
+    for (int i = 0; i < TW; ++i) {
+      if (ox0 + i < Wo) {
+        float4 o;
+        o.x = apply_act<true>(acc[i].x, act);
+        o.y = apply_act<true>(acc[i].y, act);
+        o.z = apply_act<true>(acc[i].z, act);
+        o.w = apply_act<true>(acc[i].w, act);
+        st4f(out + (((long)b * Ho + oy) * Wo + ox0 + i) * C + c, o);
+        if (pool_sum != nullptr) {
+          // sum what the next layer will actually read (bf16-rounded when T is bf16)
+          if constexpr (sizeof(T) == 2) {
+            const float2 r0 = unpack_bf16x2(pack_bf16x2(o.x, o.y)), r1 = unpack_bf16x2(pack_bf16x2(o.z, o.w));
+            ps.x += r0.x; ps.y += r0.y; ps.z += r1.x; ps.w += r1.y;
+          } else {
+            ps.x += o.x; ps.y += o.y; ps.z += o.z; ps.w += o.w;
+          }
         }
       }
     }
@@ -474,6 +484,18 @@ int dwconv_ln(const void* x, int in_dtype, const float* wgt, const float* bias, 
               cudaStream_t stream) {
   TFIMM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "dwconv_ln: need C%%4==0 (C=%d)", C);
   TFIMM_CHECK_ARG(ks == 7, "dwconv_ln: only kernel size 7 is instantiated (got %d)", ks);
+  {
+    // Fast path: channel-slab / cluster kernel (dwconv_ln_sm100.cu) whenever C splits into 1/2/4/8 slabs of
+    // 96 or 128 channels -- every registered ConvNeXt up to `base`.  TFIMM_B200_DWCONV=generic disables it.
+    static const bool force_generic = [] {
+      const char* e = getenv("TFIMM_B200_DWCONV");
+      return e != nullptr && e[0] == 'g';
+    }();
+    if (!force_generic) {
+      const int st = dwconv7_ln_cluster(x, in_dtype, wgt, bias, gamma, beta, out, out_dtype, B, H, W, C, eps, stream);
+      if (st != kUnsupported) return st;
+    }
+  }
   constexpr int TW = 7;
   // warps per CTA limited by the [TW][C] fp32 stash per warp
   const size_t per_warp = (size_t)TW * C * sizeof(float);
@@ -519,8 +541,15 @@ int dwconv_bias_act(const void* x, int dtype, const float* wgt, const float* bia
   TFIMM_CHECK_ARG((ks == 3 || ks == 5 || ks == 7) && (stride == 1 || stride == 2),
                   "dwconv: kernel size 3/5/7 and stride 1/2 are instantiated (got k=%d s=%d)", ks, stride);
   TFIMM_CHECK_ARG(dtype == kBF16 || dtype == kF32, "dwconv: dtype must be bf16 or f32");
+  {
+    // channel-pair / register-prefetch kernel (dwconv_act_sm100.cu) for k in {3,5}; the kernel below is the
+    // generic fallback (k = 7).
+    const int st = dwconv_bias_act_pairs(x, dtype, wgt, bias, out, pool_sum, B, H, W, C, ks, stride, pad_t, pad_l,
+                                         Ho, Wo, act, stream);
+    if (st != kUnsupported) return st;
+  }
   constexpr int TW = 4;
-  const long units = (long)B * Ho * ((Wo + TW - 1) / TW) * ((C + 127) / 128);
+  const long units = (long)B * Ho * ((C + 127) / 128);
   const unsigned grid = (unsigned)((units + 3) / 4);
 #define TFIMM_DW(T, KS, ST)                                                                              \
   dwconv_act_kernel<T, KS, ST, TW><<<grid, 128, 0, stream>>>(reinterpret_cast<const T*>(x), wgt, bias,    \

@@ -1,0 +1,166 @@
+// Depthwise k x k convolution + folded-BN bias + activation (+ fused squeeze sums) for the MBConv families:
+// PadDepthwiseConv2D -> BatchNormalization -> act  [-> reduce_mean for SqueezeExcite]
+// (tfimm/architectures/efficientnet_blocks.py:312-323, 393-404, 241-242; tfimm/layers/conv.py:91-148).
+//
+// HBM-bound (9-25 MACs per element), so the design goal is memory-level parallelism, not FLOPs:
+//   * one warp = one output row x 64 channels; a lane owns a channel PAIR (4-byte bf16x2 accesses, 128 B per
+//     warp instruction), its k*k taps stay in registers as packed fp32x2 for the whole row (FFMA2 math)
+//   * the row is walked in strips of TW output pixels; the k x ((TW-1)*s + k) raw input window of strip i+1
+//     is loaded into a second register buffer BEFORE strip i is computed, so every lane keeps 15-55
+//     independent loads in flight
+//   * squeeze sums accumulate in registers: one atomic per channel per row
+#include "common.cuh"
+
+namespace tfimm {
+namespace {
+
+template <typename T>
+struct RawPair;
+template <>
+struct RawPair<__nv_bfloat16> {
+  using type = uint32_t;
+  static __device__ __forceinline__ type load(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+  static __device__ __forceinline__ type zero() { return 0u; }
+  static __device__ __forceinline__ uint64_t to_f32x2(type u) {
+    return pack2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  }
+};
+template <>
+struct RawPair<float> {
+  using type = uint64_t;
+  static __device__ __forceinline__ type load(const float* p) {
+    const float2 f = *reinterpret_cast<const float2*>(p);
+    return pack2(f.x, f.y);
+  }
+  static __device__ __forceinline__ type zero() { return pack2(0.f, 0.f); }
+  static __device__ __forceinline__ uint64_t to_f32x2(type u) { return u; }
+};
+
+template <typename T, int KS, int STRIDE, int TW>
+__global__ void __launch_bounds__(128)
+dwconv_act_pairs_kernel(const T* __restrict__ x, const float* __restrict__ wgt /*[KS*KS][C]*/,
+                        const float* __restrict__ bias, T* __restrict__ out, float* __restrict__ pool_sum, int B,
+                        int H, int W, int C, int Ho, int Wo, int pad_t, int pad_l, int act) {
+  using RP = RawPair<T>;
+  using Raw = typename RP::type;
+  constexpr int IW = (TW - 1) * STRIDE + KS;  // input columns feeding one strip
+  const int cgroups = (C + 63) >> 6;
+  const long unit = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const long units = (long)B * Ho * cgroups;
+  if (unit >= units) return;
+  const int lane = threadIdx.x & 31;
+  const int cg = (int)(unit % cgroups);
+  const long t = unit / cgroups;
+  const int oy = (int)(t % Ho);
+  const int b = (int)(t / Ho);
+  const int c = cg * 64 + lane * 2;
+  if (c >= C) return;
+
+  uint64_t w[KS * KS];
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) w[i] = pack2(__ldg(wgt + (size_t)i * C + c), __ldg(wgt + (size_t)i * C + c + 1));
+  const uint64_t bv = bias != nullptr ? pack2(__ldg(bias + c), __ldg(bias + c + 1)) : pack2(0.f, 0.f);
+
+  const T* img = x + (long)b * H * W * C + c;
+  auto load_window = [&](int ox0, Raw (&buf)[KS][IW]) {
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      const int iy = oy * STRIDE + ky - pad_t;
+      const bool row_ok = iy >= 0 && iy < H;
+#pragma unroll
+      for (int ix = 0; ix < IW; ++ix) {
+        const int gx = ox0 * STRIDE + ix - pad_l;
+        buf[ky][ix] = (row_ok && gx >= 0 && gx < W) ? RP::load(img + ((long)iy * W + gx) * C) : RP::zero();
+      }
+    }
+  };
+
+  float ps0 = 0.f, ps1 = 0.f;
+  Raw nxt[KS][IW];
+  load_window(0, nxt);
+#pragma unroll 1
+  for (int ox0 = 0; ox0 < Wo; ox0 += TW) {
+    Raw cur[KS][IW];
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+      for (int ix = 0; ix < IW; ++ix) cur[ky][ix] = nxt[ky][ix];
+    if (ox0 + TW < Wo) load_window(ox0 + TW, nxt);  // in flight while this strip is computed
+
+    uint64_t acc[TW];
+#pragma unroll
+    for (int i = 0; i < TW; ++i) acc[i] = bv;
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+      for (int ix = 0; ix < IW; ++ix) {
+        const uint64_t v = RP::to_f32x2(cur[ky][ix]);
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          if ((ix - kx) >= 0 && (ix - kx) % STRIDE == 0 && (ix - kx) / STRIDE < TW)
+            acc[(ix - kx) / STRIDE] = fma2(v, w[ky * KS + kx], acc[(ix - kx) / STRIDE]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TW; ++i) {
+      if (ox0 + i < Wo) {
+        float a0, a1;
+        unpack2(acc[i], a0, a1);
+        T* dst = out + (((long)b * Ho + oy) * Wo + ox0 + i) * C + c;
+        if constexpr (sizeof(T) == 2) {
+          a0 = apply_act<false>(a0, act);
+          a1 = apply_act<false>(a1, act);
+          const uint32_t packed = pack_bf16x2(a0, a1);
+          *reinterpret_cast<uint32_t*>(dst) = packed;
+          if (pool_sum != nullptr) {  // sum what the next layer actually reads (bf16-rounded)
+            const float2 r = unpack_bf16x2(packed);
+            ps0 += r.x;
+            ps1 += r.y;
+          }
+        } else {
+          a0 = apply_act<true>(a0, act);
+          a1 = apply_act<true>(a1, act);
+          *reinterpret_cast<float2*>(dst) = make_float2(a0, a1);
+          ps0 += a0;
+          ps1 += a1;
+        }
+      }
+    }
+  }
+  if (pool_sum != nullptr) {
+    atomicAdd(pool_sum + (long)b * C + c, ps0);
+    atomicAdd(pool_sum + (long)b * C + c + 1, ps1);
+  }
+}
+
+}  // namespace
+
+int dwconv_bias_act_pairs(const void* x, int dtype, const float* wgt, const float* bias, void* out, float* pool_sum,
+                          int B, int H, int W, int C, int ks, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                          int act, cudaStream_t stream) {
+  if (C % 2 != 0 || !(ks == 3 || ks == 5) || !(stride == 1 || stride == 2)) return kUnsupported;
+  constexpr int TW = 4;
+  const long units = (long)B * Ho * ((C + 63) / 64);
+  const unsigned grid = (unsigned)((units + 3) / 4);
+#define TFIMM_DWP(T, KS, ST)                                                                                 \
+  dwconv_act_pairs_kernel<T, KS, ST, TW><<<grid, 128, 0, stream>>>(reinterpret_cast<const T*>(x), wgt, bias, \
+                                                                  reinterpret_cast<T*>(out), pool_sum, B, H, W, C, \
+                                                                  Ho, Wo, pad_t, pad_l, act)
+#define TFIMM_DWP_T(T)                                   \
+  do {                                                   \
+    if (ks == 3 && stride == 1) TFIMM_DWP(T, 3, 1);      \
+    else if (ks == 3) TFIMM_DWP(T, 3, 2);                \
+    else if (stride == 1) TFIMM_DWP(T, 5, 1);            \
+    else TFIMM_DWP(T, 5, 2);                             \
+  } while (0)
+  if (dtype == kBF16) TFIMM_DWP_T(__nv_bfloat16);
+  else if (dtype == kF32) TFIMM_DWP_T(float);
+  else return kUnsupported;
+#undef TFIMM_DWP_T
+#undef TFIMM_DWP
+  TFIMM_LAUNCH_OK("dwconv_act_pairs_kernel");
+  return kOk;
+}
+
+}  // namespace tfimm

@@ -16,4 +16,5 @@ from .utils import (  # noqa: F401
     set_dir,
     set_model_cache,
 )
+from . import parallel, serving  # noqa: F401
 from .version import __version__  # noqa: F401

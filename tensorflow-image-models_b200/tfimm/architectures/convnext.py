@@ -55,6 +55,7 @@ class ConvNeXtConfig(ModelConfig):
 
 class ConvNeXt(Model):
     cfg_class = ConvNeXtConfig
+    accepts_uint8 = True
 
     def __init__(self, cfg: ConvNeXtConfig, *args, **kwargs):
         if isinstance(cfg, dict):
@@ -140,7 +141,7 @@ class ConvNeXt(Model):
         B, H, W, _ = x.shape
         adt, rdt, eps = self.act_dtype, torch.float32, P["eps"]
         H, W = H // c.patch_size, W // c.patch_size
-        patches = ops.patchify(x, c.patch_size, adt)
+        patches = self._patchify(x, c.patch_size)
         y = ops.gemm(patches, P["stem_w"], bias=P["stem_b"])
         xs = ops.layernorm(y, *P["stem_n"], eps, rdt)  # residual stream (B*H*W, C) fp32
         if return_features:

@@ -97,6 +97,7 @@ def window_tables(h: int, w: int, ws: int, shift: int):
 
 class SwinTransformer(Model):
     cfg_class = SwinTransformerConfig
+    accepts_uint8 = True
 
     def __init__(self, cfg: SwinTransformerConfig, *args, **kwargs):
         if isinstance(cfg, dict):
@@ -282,7 +283,7 @@ class SwinTransformer(Model):
         features = OrderedDict()
         B = x.shape[0]
         adt, rdt, eps = self.act_dtype, torch.float32, P["eps"]
-        patches = ops.patchify(x, c.patch_size, adt)
+        patches = self._patchify(x, c.patch_size)
         y = ops.gemm(patches, P["pe_w"], bias=P["pe_b"])
         xs = ops.layernorm(y, *P["pe_n"], eps, rdt) if P["pe_n"] is not None else ops.cast(y, rdt)
         if return_features:

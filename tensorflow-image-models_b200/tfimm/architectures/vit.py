@@ -83,6 +83,7 @@ class ViTConfig(ModelConfig):
 
 class ViT(Model):
     cfg_class = ViTConfig
+    accepts_uint8 = True
 
     def __init__(self, cfg: ViTConfig, *args, **kwargs):
         if isinstance(cfg, dict):
@@ -184,7 +185,7 @@ class ViT(Model):
             raise ValueError(f"Input size {(H, W)} does not match the model's {tuple(c.input_size)}; "
                              "create the model with interpolate_input=True to allow this.")
         gh, gw = H // c.patch_size, W // c.patch_size
-        patches = ops.patchify(x, c.patch_size, self.act_dtype)
+        patches = self._patchify(x, c.patch_size)
         tok = ops.gemm(patches, P["pe_w"], bias=P["pe_b"])
         pos = P["pos"]
         if (gh, gw) != c.grid_size:

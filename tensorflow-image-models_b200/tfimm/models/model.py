@@ -210,11 +210,36 @@ class Model:
             x = torch.from_numpy(np.ascontiguousarray(x))
         if x.dim() == 3:
             x = x[None]
+        if x.dtype == torch.uint8:
+            # raw pixels: create_preprocessing's (x/255 - mean)/std is fused into the first kernel
+            # (reference tfimm/models/factory.py:153-169); see _patchify.
+            if not self.accepts_uint8:
+                raise TypeError(f"{type(self).__name__} takes preprocessed float images "
+                                "(fused uint8 preprocessing is implemented for the patchify families).")
+            return x.to(self.device, non_blocking=True).contiguous()
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
         if self.precision == "fp32" and x.dtype != torch.float32:
             x = x.float()
         return x.to(self.device, non_blocking=True).contiguous()
+
+    accepts_uint8 = False
+
+    def _patchify(self, x, patch_size):
+        """Non-overlapping patch gather; uint8 input gets the model's preprocessing fused in."""
+        from ..backend import ops
+
+        if x.dtype != torch.uint8:
+            return ops.patchify(x, patch_size, self.act_dtype)
+        if getattr(self, "_pre_stats", None) is None or self._pre_stats[0].device != x.device:
+            n = self.cfg.in_channels
+
+            def cyc(v):
+                return torch.tensor((list(v) * (n // len(v) + 1))[:n], dtype=torch.float32, device=x.device)
+
+            self._pre_stats = (cyc(self.cfg.mean), 1.0 / cyc(self.cfg.std))
+        mean, inv_std = self._pre_stats
+        return ops.patchify(x, patch_size, self.act_dtype, mean=mean, inv_std=inv_std, scale=1.0 / 255.0)
 
     # ------------------------------------------------------------------ public forward API
     @property
@@ -236,6 +261,39 @@ class Model:
         if training:
             raise NotImplementedError("tfimm_b200 is an inference engine: training=True is not supported.")
         return self.call(x, training=False, return_features=return_features)
+
+    def cuda_graph(self, batch_size: int, input_size=None, dtype=torch.float32):
+        """Captures one forward pass (fixed batch / input size) into a CUDA graph and returns a callable
+        ``f(x) -> logits`` that copies ``x`` into the graph's static input and replays it: the ~90-400 kernel
+        launches of a forward become one graph launch, which removes the host-side launch gaps (this is the
+        B200-native replacement for the reference's ``tf.function(jit_compile=True)`` wrapper,
+        tfimm/utils/profile.py:88-90).  The returned tensor is overwritten by the next call."""
+        from ..backend import ops
+
+        self._ensure_plan()
+        h, w = input_size or self.cfg.input_size
+        static_in = torch.zeros((batch_size, h, w, self.cfg.in_channels), device=self.device, dtype=dtype)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up: function attributes, allocator pools, tensor-map driver entry point
+                self(static_in)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        before = ops.launch_count
+        with torch.cuda.graph(graph):
+            static_out = self(static_in)
+        launches = ops.launch_count - before
+
+        def run(x):
+            static_in.copy_(x, non_blocking=True)
+            graph.replay()
+            ops.launch_count += launches
+            return static_out
+
+        run.graph, run.static_input, run.static_output, run.launches = graph, static_in, static_out, launches
+        return run
 
     def get_config(self):
         import dataclasses

@@ -280,7 +280,8 @@ def test_dwconv7x7_ln(C, H, W, in_dtype, out_dtype):
     wt = wgt.view(7, 7, C).permute(2, 0, 1)[:, None]  # (C,1,7,7)
     y = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=3, groups=C).permute(0, 2, 3, 1)
     ref = torch.nn.functional.layer_norm(y, (C,), gamma, beta, 1e-6).reshape(-1, C)
-    tol = 2e-4 if out_dtype == torch.float32 else 2.0 ** -8 * ref.abs().max().item() + 1e-3
+    # bf16 out: one output rounding, plus (cluster kernel) the conv input staged in smem as bf16
+    tol = 2e-4 if out_dtype == torch.float32 else 2.0 ** -7 * ref.abs().max().item() + 1e-3
     assert (out.float() - ref).abs().max().item() < tol
 
 

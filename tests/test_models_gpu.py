@@ -261,3 +261,59 @@ def test_engine_matches_committed_golden_logits(fixture, precision):
     rel, ab = _nerr(out, torch.from_numpy(data["logits"]))
     print(f"{fixture} {precision}: normalised {rel:.3e} abs {ab:.3e}")
     assert rel < (FP32_TOL if precision == "fp32" else 3e-2)
+
+
+def test_cuda_graph_replay_matches_eager():
+    import tfimm
+    from oracle import params
+    from oracle import vit as ovit
+
+    model = tfimm.create_model("vit_tiny_patch16_224", precision="bf16", device="cuda", nb_blocks=3)
+    model.load_weights_dict(params.random_params(ovit.param_shapes(model.cfg), seed=9))
+    fwd = model.cuda_graph(4)
+    for seed in (1, 2):
+        x = params.test_images(4, 224, 224, seed=seed).cuda()
+        eager = model(x).clone()
+        replay = fwd(x).clone()
+        assert torch.equal(eager, replay)
+    assert fwd.launches > 0
+
+
+@pytest.mark.parametrize("name,family", [("vit_tiny_patch16_224", "vit"), ("convnext_tiny", "convnext"),
+                                         ("swin_tiny_patch4_window7_224", "swin")])
+def test_fused_uint8_preprocessing_equals_create_preprocessing(name, family):
+    """model(uint8 pixels) == model(create_preprocessing(name)(pixels))  (reference factory.py:153-169)."""
+    import importlib
+
+    import numpy as np
+
+    import tfimm
+    from oracle import params
+
+    omod = importlib.import_module(f"oracle.{family}")
+    model = tfimm.create_model(name, precision="fp32", device="cuda")
+    model.load_weights_dict(params.random_params(omod.param_shapes(model.cfg), seed=21))
+    raw = np.random.default_rng(5).integers(0, 256, (2, 224, 224, 3), dtype=np.uint8)
+    pre = tfimm.create_preprocessing(name)
+    a = model(torch.from_numpy(raw).cuda())
+    b = model(torch.from_numpy(pre(raw)).cuda())
+    assert _nerr(a, b)[0] < 1e-5
+
+
+def test_inference_pipeline_matches_direct_calls():
+    import tfimm
+    from oracle import params
+    from oracle import vit as ovit
+    from tfimm.serving import InferencePipeline
+
+    model = tfimm.create_model("vit_tiny_patch16_224", precision="bf16", device="cuda", nb_blocks=2)
+    model.load_weights_dict(params.random_params(ovit.param_shapes(model.cfg), seed=22))
+    pipe = InferencePipeline(model, 4, depth=2)
+    batches = [params.test_images(4, 224, 224, seed=s).pin_memory() for s in (1, 2, 3, 4, 5)]
+    outs = []
+    for xb in batches:
+        o = pipe.submit(xb)
+        pipe.synchronize()
+        outs.append(o.clone())
+    for xb, o in zip(batches, outs):
+        assert torch.equal(model(xb.cuda()).cpu(), o)
