@@ -121,13 +121,37 @@ def _oracle_forward(model_name):
     return cfg, mod
 
 
+def host_cores():
+    """CPU threads this process may actually use: the scheduler affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the whole host and oversubscribes a quota-limited container 10x)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                quota = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    n = min(n, max(1, quota // period))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 def cpu_oracle_throughput(model_name, batch, iters, warmup=1):
-    """images/sec of the torch-CPU oracle (the reference's CPU stand-in) on all host cores."""
+    """images/sec of the torch-CPU oracle (the reference's CPU stand-in) on the host cores we may use."""
     import torch
 
     from oracle import params
 
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     cfg, mod = _oracle_forward(model_name)
     w = params.random_params(mod.param_shapes(cfg), seed=0)
@@ -183,6 +207,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout and would precede the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     model = tfimm.create_model(args.model, precision="bf16", device=dev, seed=0)

@@ -2,13 +2,16 @@
 // PadDepthwiseConv2D -> BatchNormalization -> act  [-> reduce_mean for SqueezeExcite]
 // (tfimm/architectures/efficientnet_blocks.py:312-323, 393-404, 241-242; tfimm/layers/conv.py:91-148).
 //
-// HBM-bound (9-25 MACs per element), so the design goal is memory-level parallelism, not FLOPs:
+// HBM-bound by arithmetic (9-25 MACs per element); the first version of this kernel was *instruction* bound
+// (ncu: 144 issued instructions per output pair, profiles/r01_*), so the design goals are memory-level
+// parallelism and a lean inner loop:
 //   * one warp = one output row x 64 channels; a lane owns a channel PAIR (4-byte bf16x2 accesses, 128 B per
 //     warp instruction), its k*k taps stay in registers as packed fp32x2 for the whole row (FFMA2 math)
 //   * the row is walked in strips of TW output pixels; the k x ((TW-1)*s + k) raw input window of strip i+1
-//     is loaded into a second register buffer BEFORE strip i is computed, so every lane keeps 15-55
-//     independent loads in flight
-//   * squeeze sums accumulate in registers: one atomic per channel per row
+//     is loaded into a second register buffer BEFORE strip i is computed (15-55 independent loads in flight)
+//   * interior strips (whole window inside the image) take a branch-free path with per-row base pointers;
+//     only border strips pay for bounds predicates
+//   * activation on packed pairs; squeeze sums accumulate in registers: one atomic per channel per row
 #include "common.cuh"
 
 namespace tfimm {
@@ -36,6 +39,17 @@ struct RawPair<float> {
   static __device__ __forceinline__ uint64_t to_f32x2(type u) { return u; }
 };
 
+template <bool kFast>
+__device__ __forceinline__ uint64_t act_pair(uint64_t v, int act) {
+  if (kFast) {
+    if (act == kActSwish) return swish_fast2(v);
+    if (act == kActNone) return v;
+  }
+  float a, b;
+  unpack2(v, a, b);
+  return pack2(apply_act<!kFast>(a, act), apply_act<!kFast>(b, act));
+}
+
 template <typename T, int KS, int STRIDE, int TW>
 __global__ void __launch_bounds__(128)
 dwconv_act_pairs_kernel(const T* __restrict__ x, const float* __restrict__ wgt /*[KS*KS][C]*/,
@@ -61,21 +75,42 @@ dwconv_act_pairs_kernel(const T* __restrict__ x, const float* __restrict__ wgt /
   for (int i = 0; i < KS * KS; ++i) w[i] = pack2(__ldg(wgt + (size_t)i * C + c), __ldg(wgt + (size_t)i * C + c + 1));
   const uint64_t bv = bias != nullptr ? pack2(__ldg(bias + c), __ldg(bias + c + 1)) : pack2(0.f, 0.f);
 
-  const T* img = x + (long)b * H * W * C + c;
+  // per-tap-row base pointers (column 0 of the image row) and validity
+  const T* rowp[KS];
+  bool rowok[KS];
+  bool rows_all_ok = true;
+#pragma unroll
+  for (int ky = 0; ky < KS; ++ky) {
+    const int iy = oy * STRIDE + ky - pad_t;
+    rowok[ky] = iy >= 0 && iy < H;
+    rows_all_ok = rows_all_ok && rowok[ky];
+    rowp[ky] = x + (((long)b * H + (rowok[ky] ? iy : 0)) * W) * C + c;
+  }
+
   auto load_window = [&](int ox0, Raw (&buf)[KS][IW]) {
+    const int gx0 = ox0 * STRIDE - pad_l;
+    if (rows_all_ok && gx0 >= 0 && gx0 + IW <= W) {
+      // interior: no predicates, one pointer bump per column
 #pragma unroll
-    for (int ky = 0; ky < KS; ++ky) {
-      const int iy = oy * STRIDE + ky - pad_t;
-      const bool row_ok = iy >= 0 && iy < H;
+      for (int ky = 0; ky < KS; ++ky) {
+        const T* p = rowp[ky] + (long)gx0 * C;
 #pragma unroll
-      for (int ix = 0; ix < IW; ++ix) {
-        const int gx = ox0 * STRIDE + ix - pad_l;
-        buf[ky][ix] = (row_ok && gx >= 0 && gx < W) ? RP::load(img + ((long)iy * W + gx) * C) : RP::zero();
+        for (int ix = 0; ix < IW; ++ix) buf[ky][ix] = RP::load(p + (long)ix * C);
+      }
+    } else {
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+        for (int ix = 0; ix < IW; ++ix) {
+          const int gx = gx0 + ix;
+          buf[ky][ix] = (rowok[ky] && gx >= 0 && gx < W) ? RP::load(rowp[ky] + (long)gx * C) : RP::zero();
+        }
       }
     }
   };
 
-  float ps0 = 0.f, ps1 = 0.f;
+  uint64_t ps = pack2(0.f, 0.f);
+  T* orow = out + (((long)b * Ho + oy) * Wo) * C + c;
   Raw nxt[KS][IW];
   load_window(0, nxt);
 #pragma unroll 1
@@ -105,32 +140,27 @@ dwconv_act_pairs_kernel(const T* __restrict__ x, const float* __restrict__ wgt /
 #pragma unroll
     for (int i = 0; i < TW; ++i) {
       if (ox0 + i < Wo) {
+        const uint64_t a = act_pair<sizeof(T) == 2>(acc[i], act);
         float a0, a1;
-        unpack2(acc[i], a0, a1);
-        T* dst = out + (((long)b * Ho + oy) * Wo + ox0 + i) * C + c;
+        unpack2(a, a0, a1);
+        T* dst = orow + (long)(ox0 + i) * C;
         if constexpr (sizeof(T) == 2) {
-          a0 = apply_act<false>(a0, act);
-          a1 = apply_act<false>(a1, act);
           const uint32_t packed = pack_bf16x2(a0, a1);
           *reinterpret_cast<uint32_t*>(dst) = packed;
-          if (pool_sum != nullptr) {  // sum what the next layer actually reads (bf16-rounded)
-            const float2 r = unpack_bf16x2(packed);
-            ps0 += r.x;
-            ps1 += r.y;
-          }
+          // squeeze sums see what the next layer actually reads (bf16-rounded)
+          if (pool_sum != nullptr) ps = add2(ps, RP::to_f32x2(packed));
         } else {
-          a0 = apply_act<true>(a0, act);
-          a1 = apply_act<true>(a1, act);
           *reinterpret_cast<float2*>(dst) = make_float2(a0, a1);
-          ps0 += a0;
-          ps1 += a1;
+          ps = add2(ps, a);
         }
       }
     }
   }
   if (pool_sum != nullptr) {
-    atomicAdd(pool_sum + (long)b * C + c, ps0);
-    atomicAdd(pool_sum + (long)b * C + c + 1, ps1);
+    float p0, p1;
+    unpack2(ps, p0, p1);
+    atomicAdd(pool_sum + (long)b * C + c, p0);
+    atomicAdd(pool_sum + (long)b * C + c + 1, p1);
   }
 }
 
@@ -140,22 +170,23 @@ int dwconv_bias_act_pairs(const void* x, int dtype, const float* wgt, const floa
                           int B, int H, int W, int C, int ks, int stride, int pad_t, int pad_l, int Ho, int Wo,
                           int act, cudaStream_t stream) {
   if (C % 2 != 0 || !(ks == 3 || ks == 5) || !(stride == 1 || stride == 2)) return kUnsupported;
-  constexpr int TW = 4;
   const long units = (long)B * Ho * ((C + 63) / 64);
   const unsigned grid = (unsigned)((units + 3) / 4);
-#define TFIMM_DWP(T, KS, ST)                                                                                 \
+#define TFIMM_DWP(T, KS, ST, TW)                                                                             \
   dwconv_act_pairs_kernel<T, KS, ST, TW><<<grid, 128, 0, stream>>>(reinterpret_cast<const T*>(x), wgt, bias, \
                                                                   reinterpret_cast<T*>(out), pool_sum, B, H, W, C, \
                                                                   Ho, Wo, pad_t, pad_l, act)
-#define TFIMM_DWP_T(T)                                   \
+  // strip width: 8 outputs for the bf16 3x3/s1 case (window 10 columns x 3 rows per buffer), 4 otherwise --
+  // chosen so that the two raw-window register buffers + taps stay under 255 registers without spilling
+#define TFIMM_DWP_T(T, TW31)                             \
   do {                                                   \
-    if (ks == 3 && stride == 1) TFIMM_DWP(T, 3, 1);      \
-    else if (ks == 3) TFIMM_DWP(T, 3, 2);                \
-    else if (stride == 1) TFIMM_DWP(T, 5, 1);            \
-    else TFIMM_DWP(T, 5, 2);                             \
+    if (ks == 3 && stride == 1) TFIMM_DWP(T, 3, 1, TW31); \
+    else if (ks == 3) TFIMM_DWP(T, 3, 2, 4);             \
+    else if (stride == 1) TFIMM_DWP(T, 5, 1, 4);         \
+    else TFIMM_DWP(T, 5, 2, 4);                          \
   } while (0)
-  if (dtype == kBF16) TFIMM_DWP_T(__nv_bfloat16);
-  else if (dtype == kF32) TFIMM_DWP_T(float);
+  if (dtype == kBF16) TFIMM_DWP_T(__nv_bfloat16, 8);
+  else if (dtype == kF32) TFIMM_DWP_T(float, 4);
   else return kUnsupported;
 #undef TFIMM_DWP_T
 #undef TFIMM_DWP

@@ -61,17 +61,40 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat1
     cp_async_16(sV + off, src + 2 * H * kWDH, valid);
   }
   cp_async_commit();
-  cp_async_wait<0>();
-  __syncwarp();
 
   const int g = lane >> 2, t = lane & 3;
   const float* bias_h = bias + (long)h * N * N;
+  // Relative-position bias of one 16-query tile in mma accumulator layout.  It only depends on (head, row,
+  // key), so the tile for m-tile mt+1 is fetched while m-tile mt is being processed (and the first one while
+  // the q/k/v rows are still in flight): the L2 latency of these scattered 4-byte loads never stalls the math.
+  auto load_bias_tile = [&](int mt, float (&bz)[8][4]) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = min(nt * 8 + 2 * t + (e & 1), N - 1);
+        const int row = min(mt * 16 + g + ((e >> 1) ? 8 : 0), N - 1);
+        bz[nt][e] = __ldg(bias_h + (long)row * N + key);
+      }
+    }
+  };
+  float bz_next[8][4];
+  load_bias_tile(0, bz_next);
+  cp_async_wait<0>();
+  __syncwarp();
+
   const int mtiles = (N + 15) >> 4;
   const int ntiles = (N + 7) >> 3;   // key tiles with at least one valid key (<= 8)
   const float l2e = 1.4426950408889634f;
 
 #pragma unroll 1
   for (int mt = 0; mt < mtiles; ++mt) {
+    float bz[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bz[nt][e] = bz_next[nt][e];
+    if (mt + 1 < mtiles) load_bias_tile(mt + 1, bz_next);
     uint32_t qf[2][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
@@ -104,7 +127,7 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat1
         const int row = (e >> 1) ? r1 : r0;
         float val = -INFINITY;
         if (key < N && row < N) {
-          val = s[nt][e] * scale + __ldg(bias_h + (long)row * N + key);
+          val = fmaf(s[nt][e], scale, bz[nt][e]);
           if (labels != nullptr && s_lab[warp][key] != ((e >> 1) ? lab1 : lab0)) val += -100.0f;
         } else if (key < N) {
           val = 0.f;  // padded query rows: keep finite, result is discarded

@@ -93,8 +93,9 @@ def test_depthwise_kernel_layout():
 def test_roll_and_dense_and_softmax():
     x = torch.arange(5.0)
     assert tf.roll(x, -2, 0).tolist() == [2, 3, 4, 0, 1]  # y[i] = x[(i + 2) mod n]
-    a, w = torch.randn(2, 3, 4), torch.randn(4, 5)
-    assert torch.allclose(tf.dense(a, w), torch.einsum("bnk,kj->bnj", a, w))
+    g = torch.Generator().manual_seed(0)
+    a, w = torch.randn(2, 3, 4, generator=g), torch.randn(4, 5, generator=g)
+    assert torch.allclose(tf.dense(a, w), torch.einsum("bnk,kj->bnj", a, w), atol=1e-5)
     s = tf.softmax(torch.tensor([[1000.0, 1000.0]]))
     assert torch.allclose(s, torch.tensor([[0.5, 0.5]]))
 
@@ -365,3 +366,26 @@ def test_oracle_reproduces_committed_golden_logits(fixture):
     with torch.no_grad():
         y = mod.forward(cfg, w, x)
     assert nerr(y, torch.from_numpy(data["logits"])) < 1e-5
+
+
+def test_pytorch_state_dict_ingestion_reproduces_torchvision_resnet():
+    """N1: a PyTorch state_dict in timm naming (torchvision's ResNet uses the same names) converted by
+    tfimm.utils.timm (rules of reference utils/timm.py:39-106) and run through the oracle gives torchvision's
+    own logits."""
+    from tfimm.utils.timm import convert_state_dict, pytorch_key
+
+    assert pytorch_key("remove/fc/kernel") == "fc.weight"
+    assert pytorch_key("layer1/0/downsample/1/moving_variance") == "layer1.0.downsample.1.running_var"
+    tv = _randomize(torchvision.models.resnet50(), 6).float()
+    model = tfimm.create_model("resnet50", device="cpu")
+    weights, missing, unexpected = convert_state_dict(model, tv.state_dict())
+    assert not missing and not unexpected
+    assert set(weights) == set(model.params)
+    model.load_weights_dict(weights)
+    x = _images(1, 96, 96).float()
+    with torch.no_grad():
+        ref = tv(x.permute(0, 3, 1, 2))
+    got = oresnet.forward(model.cfg, {k: v for k, v in model.params.items()}, x)
+    assert nerr(got, ref) < 1e-4
+    with pytest.raises(AttributeError):
+        convert_state_dict(tfimm.create_model("resnet18", device="meta"), {"conv1.weight": np.zeros((64, 3, 7, 7))})
