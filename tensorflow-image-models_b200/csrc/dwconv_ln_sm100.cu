@@ -1,20 +1,25 @@
 // ConvNeXt block head on sm_100a:  ZeroPadding2D(3) -> DepthwiseConv2D(7x7, bias) -> LayerNorm over C
 // (tfimm/architectures/convnext.py:189-198, 219-223), channel-slab / thread-block-cluster formulation.
 //
-// A depthwise 7x7 is 49 MACs per element: FP32-FMA bound on the CUDA cores, not HBM bound, *if* the taps
-// and the input halo are read from on-chip memory.  LayerNorm then needs every channel of a pixel.  Both are
-// reconciled by splitting the channels of one 14x7 pixel tile over the CTAs of a cluster:
+// A depthwise 7x7 is 49 MACs per element: FP32-FMA bound on the CUDA cores (not HBM bound) *if* the taps and
+// the input halo come from on-chip memory and the instruction stream is mostly FMAs.  LayerNorm needs every
+// channel of a pixel.  Both are reconciled by splitting the channels of one 14x7 pixel tile over the CTAs of a
+// thread-block cluster; clusters are persistent and walk over the tiles of the batch:
 //
-//   CTA (cluster rank r)  owns channels [r*CS, (r+1)*CS)  (CS = 96 or 128) of a 14(rows) x 7(cols) output tile
-//     A. stage the 20x13 input halo of its channel slab in shared memory as bf16 (zero outside the image)
-//     B. each thread keeps the 49 taps of ONE channel pair in registers (packed fp32x2) and slides over its
-//        share of the tile's 7-pixel row strips: 343 FFMA2 per strip, operands from smem; results (+bias) go
-//        to an fp16 stash [98][CS] in shared memory (11-bit mantissa: 8x finer than the bf16 output)
-//     C. LayerNorm statistics: per-pixel partial sums over the slab, exchanged between the CTAs of the
-//        cluster through distributed shared memory (two rounds: mean, then centred second moment)
-//     D. normalise the own slab and write bf16 rows
-// ~93 KB of shared memory per CTA, so two CTAs are resident per SM and one CTA's global loads (phase A)
-// overlap the other's FMA phase.  Weights are read once per CTA instead of once per pixel strip.
+//   CTA (cluster rank r) owns channels [r*CS, (r+1)*CS) (CS = 64 or 32) of the current 14(rows) x 7(cols) tile
+//     A. ONE 4-D TMA box copy (C, W, H, B) brings the 20x13xCS fp32 input halo into shared memory; the
+//        zero padding of the convolution is the TMA out-of-bounds fill (negative / past-the-edge coordinates),
+//        so there is no index arithmetic or predicate in the load path at all
+//     B. a thread keeps the 49 taps of ONE channel pair in registers (packed fp32x2, loaded once per kernel)
+//        and computes a 2-row x 7-column output block: every 8-byte shared-memory load (one halo pixel, two
+//        channels, already fp32x2) feeds up to 14 FFMA2; 686 FFMA2 per 104 loads.  Results (+bias) go to an
+//        fp16 stash [98][CS] in shared memory (11-bit mantissa: 8x finer than the bf16 output)
+//        -> the halo buffer is free again: the TMA copy of the cluster's NEXT tile is issued here and overlaps C/D
+//     C. LayerNorm statistics: per-pixel (sum, centred second moment) of the slab, exchanged between the CTAs
+//        of the cluster through distributed shared memory and merged with the parallel-variance formula
+//     D. normalise the own slab and write bf16 rows (16 B per lane)
+// ~81 KB of shared memory and 224 threads per CTA: two CTAs per SM, so one CTA's FMA phase overlaps the
+// other's statistics / store phases.
 #include "common.cuh"
 
 #include <cooperative_groups.h>
@@ -25,211 +30,222 @@ namespace cg = cooperative_groups;
 namespace tfimm {
 namespace {
 
-constexpr int kTH = 14;              // output tile rows
-constexpr int kTW = 7;               // output tile columns (one 7-pixel strip per row)
+constexpr int kTH = 14;              // output tile rows (7 row pairs)
+constexpr int kTW = 7;               // output tile columns
 constexpr int kHH = kTH + 6;         // 20 halo rows
 constexpr int kHW = kTW + 6;         // 13 halo columns
 constexpr int kPix = kTH * kTW;      // 98
-constexpr int kThreads = 256;
+constexpr int kWarps = kTH / 2;      // one warp per output row pair
+constexpr int kThreads = kWarps * 32;
 
 template <int CS>
 struct DwCfg {
-  static constexpr int kPairs = CS / 2;                 // channel pairs per slab
-  static constexpr int kSlots = 64;                     // thread slots per row group (>= kPairs)
-  static constexpr int kHaloBytes = ((kHH * kHW * CS * 2 + 15) / 16) * 16;
-  static constexpr int kStashBytes = kPix * CS * 2;     // fp16
-  static constexpr int kStatBytes = kPix * 4 * 4;       // part_sum, part_sq, mean, rstd
-  static constexpr int kSmemBytes = kHaloBytes + kStashBytes + kStatBytes;
+  static constexpr int kPairs = CS / 2;                  // channel pairs per slab (<= 32: one lane each)
+  static constexpr int kOct = CS / 8;                    // 8-channel groups per pixel row
+  static constexpr int kPixPerWarp = 32 / kOct;          // pixels per warp step in phases C/D
+  static constexpr int kHaloBytes = kHH * kHW * CS * 4;  // fp32
+  static constexpr int kStashBytes = kPix * CS * 2;      // fp16
+  static constexpr int kStatBytes = kPix * 4 * 4;        // part_sum, part_m2, mean, rstd
+  static constexpr int kSmemBytes = kHaloBytes + kStashBytes + kStatBytes + 16;
 };
 
-__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t u) {
-  // bf16 -> fp32 is a 16-bit shift: low half -> lane 0, high half -> lane 1
-  return pack2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-}
-
-template <typename InT, int CS>
+template <int CS>
 __global__ void __launch_bounds__(kThreads, 2)
-dwconv7_ln_cluster_kernel(const InT* __restrict__ x, const float* __restrict__ wgt /*[49][C]*/,
+dwconv7_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ wgt /*[49][C]*/,
                           const float* __restrict__ bias, const float* __restrict__ gamma,
                           const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int H, int W, int C,
-                          int tiles_x, int tiles_per_img, int cluster_size, float eps) {
+                          int tiles_x, int tiles_per_img, int n_tiles, int cluster_size, float eps) {
   using Cfg = DwCfg<CS>;
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint32_t* halo = reinterpret_cast<uint32_t*>(smem);                          // [20*13][CS/2] bf16x2
-  __half2* stash = reinterpret_cast<__half2*>(smem + Cfg::kHaloBytes);         // [98][CS/2] fp16x2
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint64_t* halo = reinterpret_cast<const uint64_t*>(smem);                 // [20*13][CS/2] fp32x2
+  __half* stash = reinterpret_cast<__half*>(smem + Cfg::kHaloBytes);              // [98][CS] fp16
   float* part_sum = reinterpret_cast<float*>(smem + Cfg::kHaloBytes + Cfg::kStashBytes);
-  float* part_sq = part_sum + kPix;
-  float* s_mean = part_sq + kPix;
+  float* part_m2 = part_sum + kPix;
+  float* s_mean = part_m2 + kPix;
   float* s_rstd = s_mean + kPix;
+  const uint32_t bar = smem_u32(s_rstd + kPix);
+  const uint32_t halo_addr = smem_u32(smem);
 
+  cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int crank = blockIdx.x % cluster_size;
-  const int tile_id = blockIdx.x / cluster_size;
-  const int b = tile_id / tiles_per_img;
-  const int t_in_img = tile_id % tiles_per_img;
-  const int ty0 = (t_in_img / tiles_x) * kTH, tx0 = (t_in_img % tiles_x) * kTW;
+  const int crank = (int)cluster.block_rank();
+  const int cluster_id = blockIdx.x / cluster_size, n_clusters = gridDim.x / cluster_size;
   const int c_base = crank * CS;
 
-  // ---- A. halo tile -> smem (bf16), 4 channels per lane; loads issued in batches before any is consumed ----
-  {
-    constexpr int kQuads = CS / 4;
-    constexpr int kTotal = kHH * kHW * kQuads;
-    constexpr int kU = 8;
-    for (int base = 0; base < kTotal; base += kThreads * kU) {
-      uint2 v[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int idx = base + u * kThreads + tid;
-        v[u] = make_uint2(0u, 0u);
-        if (idx < kTotal) {
-          const int qd = idx % kQuads;
-          const int pos = idx / kQuads;
-          const int gy = ty0 + pos / kHW - 3, gx = tx0 + pos % kHW - 3;
-          if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const InT* src = x + (((long)b * H + gy) * W + gx) * C + c_base + qd * 4;
-            if constexpr (sizeof(InT) == 4) {
-              const float4 f = *reinterpret_cast<const float4*>(src);
-              v[u].x = pack_bf16x2(f.x, f.y);
-              v[u].y = pack_bf16x2(f.z, f.w);
-            } else {
-              v[u] = *reinterpret_cast<const uint2*>(src);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int idx = base + u * kThreads + tid;
-        if (idx < kTotal) *reinterpret_cast<uint2*>(halo + (size_t)(idx / kQuads) * (CS / 2) + (idx % kQuads) * 2) = v[u];
-      }
-    }
+  if (tid == 0) {
+    prefetch_tmap(&tmap_x);
+    mbar_init(bar, 1);
+    fence_mbar_init();
   }
   __syncthreads();
 
-  // ---- B. depthwise 7x7: thread = (channel pair cp, row group rg); one 7-pixel strip per tile row ----
-  {
-    const int cp = tid % Cfg::kSlots, rg = tid / Cfg::kSlots;
-    if (cp < Cfg::kPairs) {
-      const int c0 = c_base + 2 * cp;
-      uint64_t w[49];
-#pragma unroll
-      for (int t = 0; t < 49; ++t) w[t] = pack2(__ldg(wgt + (size_t)t * C + c0), __ldg(wgt + (size_t)t * C + c0 + 1));
-      const uint64_t bv = pack2(__ldg(bias + c0), __ldg(bias + c0 + 1));
-#pragma unroll 1
-      for (int oy = rg; oy < kTH; oy += kThreads / Cfg::kSlots) {
-        if (ty0 + oy >= H) break;
-        uint64_t acc[7];
-#pragma unroll
-        for (int i = 0; i < 7; ++i) acc[i] = bv;
-#pragma unroll
-        for (int ky = 0; ky < 7; ++ky) {
-          const uint32_t* row = halo + (size_t)((oy + ky) * kHW) * (CS / 2) + cp;
-#pragma unroll
-          for (int ix = 0; ix < 13; ++ix) {
-            const uint64_t v = bf16x2_to_f32x2(row[(size_t)ix * (CS / 2)]);
-#pragma unroll
-            for (int kx = 0; kx < 7; ++kx) {
-              const int ox = ix - kx;
-              if (ox >= 0 && ox < 7) acc[ox] = fma2(v, w[ky * 7 + kx], acc[ox]);
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-          float a0, a1;
-          unpack2(acc[i], a0, a1);
-          stash[(size_t)(oy * kTW + i) * (CS / 2) + cp] = __floats2half2_rn(a0, a1);
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- C. LayerNorm statistics over all C channels of each pixel (cluster-wide) ----
-  cg::cluster_group cluster = cg::this_cluster();
-  const float inv_c = 1.0f / (float)C;
-  auto pixel_valid = [&](int p) { return (ty0 + p / kTW) < H && (tx0 + p % kTW) < W; };
-  // lane l reads channel pairs 2l, 2l+1 (one 8-byte access) of a pixel's slab row
-  auto load4 = [&](int p, float (&v)[4]) {
-    const uint2 u = *reinterpret_cast<const uint2*>(stash + (size_t)p * (CS / 2) + 2 * lane);
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-    const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-    v[0] = a.x; v[1] = a.y; v[2] = c2.x; v[3] = c2.y;
+  auto issue_halo = [&](int tile) {
+    const int b = tile / tiles_per_img, t = tile % tiles_per_img;
+    mbar_expect_tx(bar, Cfg::kHaloBytes);
+    tma_load_4d(halo_addr, &tmap_x, bar, c_base, (t % tiles_x) * kTW - 3, (t / tiles_x) * kTH - 3, b);
   };
-  const bool lane_on = lane * 4 < CS;
-  for (int p = warp; p < kPix; p += kThreads / 32) {
-    float s = 0.f;
-    if (lane_on && pixel_valid(p)) {
-      float v[4];
-      load4(p, v);
-      s = (v[0] + v[1]) + (v[2] + v[3]);
-    }
-    s = warp_sum(s);
-    if (lane == 0) part_sum[p] = s;
-  }
-  if (cluster_size > 1) cluster.sync(); else __syncthreads();
-  for (int p = tid; p < kPix; p += kThreads) {
-    float s = 0.f;
-    for (int r = 0; r < cluster_size; ++r)
-      s += (cluster_size > 1 ? cluster.map_shared_rank(part_sum, r) : part_sum)[p];
-    s_mean[p] = s * inv_c;
-  }
-  __syncthreads();
-  for (int p = warp; p < kPix; p += kThreads / 32) {
-    float s = 0.f;
-    if (lane_on && pixel_valid(p)) {
-      const float m = s_mean[p];
-      float v[4];
-      load4(p, v);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s += (v[j] - m) * (v[j] - m);
-    }
-    s = warp_sum(s);
-    if (lane == 0) part_sq[p] = s;
-  }
-  if (cluster_size > 1) cluster.sync(); else __syncthreads();
-  for (int p = tid; p < kPix; p += kThreads) {
-    float s = 0.f;
-    for (int r = 0; r < cluster_size; ++r)
-      s += (cluster_size > 1 ? cluster.map_shared_rank(part_sq, r) : part_sq)[p];
-    s_rstd[p] = rsqrtf(s * inv_c + eps);
-  }
-  __syncthreads();
+  int tile = cluster_id;
+  if (tid == 0 && tile < n_tiles) issue_halo(tile);
 
-  // ---- D. normalise the own slab and write (8 bytes per lane, 256 B per pixel row for CS = 128) ----
-  if (lane_on) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c_base + lane * 4));
-    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c_base + lane * 4));
-    for (int p = warp; p < kPix; p += kThreads / 32) {
-      if (!pixel_valid(p)) continue;
-      const float m = s_mean[p], rs = s_rstd[p];
-      float v[4];
-      load4(p, v);
-      uint2 u;
-      u.x = pack_bf16x2((v[0] - m) * rs * g.x + be.x, (v[1] - m) * rs * g.y + be.y);
-      u.y = pack_bf16x2((v[2] - m) * rs * g.z + be.z, (v[3] - m) * rs * g.w + be.w);
-      __nv_bfloat16* orow = out + (((long)b * H + ty0 + p / kTW) * W + tx0 + p % kTW) * C + c_base + lane * 4;
-      *reinterpret_cast<uint2*>(orow) = u;
+  // taps of this lane's channel pair: registers for the whole kernel
+  const bool pair_on = lane < Cfg::kPairs;
+  const int c0 = c_base + 2 * (pair_on ? lane : 0);
+  uint64_t w[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) w[t] = pack2(__ldg(wgt + (size_t)t * C + c0), __ldg(wgt + (size_t)t * C + c0 + 1));
+  const uint64_t bv = pack2(__ldg(bias + c0), __ldg(bias + c0 + 1));
+
+  const int q = lane / Cfg::kOct, o = lane % Cfg::kOct;  // phases C/D: pixel slot / channel octet of this lane
+  const float inv_c = 1.0f / (float)C;
+  uint32_t phase = 0;
+
+  for (; tile < n_tiles; tile += n_clusters) {
+    const int b = tile / tiles_per_img, t_in_img = tile % tiles_per_img;
+    const int ty0 = (t_in_img / tiles_x) * kTH, tx0 = (t_in_img % tiles_x) * kTW;
+    mbar_wait(bar, phase);
+    phase ^= 1;
+
+    // ---- B. depthwise 7x7: warp = output row pair, lane = channel pair ----
+    const int oy0 = 2 * warp;
+    if (pair_on && ty0 + oy0 < H) {
+      uint64_t acc0[7], acc1[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) acc0[i] = acc1[i] = bv;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint64_t* row = halo + (size_t)((oy0 + r) * kHW) * Cfg::kPairs + lane;
+#pragma unroll
+        for (int ix = 0; ix < kHW; ++ix) {
+          const uint64_t v = row[(size_t)ix * Cfg::kPairs];
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) {
+            const int ox = ix - kx;
+            if (ox >= 0 && ox < 7) {
+              if (r <= 6) acc0[ox] = fma2(v, w[r * 7 + kx], acc0[ox]);
+              if (r >= 1) acc1[ox] = fma2(v, w[(r - 1) * 7 + kx], acc1[ox]);
+            }
+          }
+        }
+      }
+      __half2* st0 = reinterpret_cast<__half2*>(stash) + (size_t)(oy0 * kTW) * Cfg::kPairs + lane;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        float a0, a1;
+        unpack2(acc0[i], a0, a1);
+        st0[(size_t)i * Cfg::kPairs] = __floats2half2_rn(a0, a1);
+        unpack2(acc1[i], a0, a1);
+        st0[(size_t)(kTW + i) * Cfg::kPairs] = __floats2half2_rn(a0, a1);
+      }
     }
+    __syncthreads();
+    // halo buffer is free: fetch the next tile of this cluster while the statistics / store phases run
+    if (tid == 0 && tile + n_clusters < n_tiles) issue_halo(tile + n_clusters);
+
+    auto pixel_valid = [&](int p) { return p < kPix && (ty0 + p / kTW) < H && (tx0 + p % kTW) < W; };
+    auto load8 = [&](int p, float (&v)[8]) {
+      const uint4 u = *reinterpret_cast<const uint4*>(stash + (size_t)p * CS + o * 8);
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uu[j]));
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+      }
+    };
+    auto oct_sum = [&](float s) {
+#pragma unroll
+      for (int off = 1; off < Cfg::kOct; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      return s;
+    };
+
+    // ---- C. slab statistics per pixel: sum and second moment about the slab mean ----
+    for (int p0 = warp * Cfg::kPixPerWarp; p0 < kPix; p0 += kWarps * Cfg::kPixPerWarp) {
+      const int p = p0 + q;
+      float v[8];
+      const bool ok = pixel_valid(p);
+      if (ok) load8(p, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+      const float s = oct_sum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])));
+      const float m = s * (1.0f / CS);
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d += (v[j] - m) * (v[j] - m);
+      d = oct_sum(d);
+      if (o == 0 && p < kPix) {
+        part_sum[p] = s;
+        part_m2[p] = ok ? d : 0.f;
+      }
+    }
+    cluster.sync();
+    // merge the slabs (Chan et al.): M2 = sum_r [ M2_r + CS * (mean_r - mean)^2 ]
+    for (int p = tid; p < kPix; p += kThreads) {
+      float s = 0.f;
+      for (int r = 0; r < cluster_size; ++r) s += cluster.map_shared_rank(part_sum, r)[p];
+      const float mean = s * inv_c;
+      float m2 = 0.f;
+      for (int r = 0; r < cluster_size; ++r) {
+        const float dm = cluster.map_shared_rank(part_sum, r)[p] * (1.0f / CS) - mean;
+        m2 += cluster.map_shared_rank(part_m2, r)[p] + (float)CS * dm * dm;
+      }
+      s_mean[p] = mean;
+      s_rstd[p] = rsqrtf(m2 * inv_c + eps);
+    }
+    __syncthreads();
+
+    // ---- D. normalise the own slab and write (8 channels = 16 B per lane) ----
+    {
+      float g[8], be[8];
+      *reinterpret_cast<float4*>(&g[0]) = __ldg(reinterpret_cast<const float4*>(gamma + c_base + o * 8));
+      *reinterpret_cast<float4*>(&g[4]) = __ldg(reinterpret_cast<const float4*>(gamma + c_base + o * 8 + 4));
+      *reinterpret_cast<float4*>(&be[0]) = __ldg(reinterpret_cast<const float4*>(beta + c_base + o * 8));
+      *reinterpret_cast<float4*>(&be[4]) = __ldg(reinterpret_cast<const float4*>(beta + c_base + o * 8 + 4));
+      for (int p0 = warp * Cfg::kPixPerWarp; p0 < kPix; p0 += kWarps * Cfg::kPixPerWarp) {
+        const int p = p0 + q;
+        if (!pixel_valid(p)) continue;
+        const float m = s_mean[p], rs = s_rstd[p];
+        float v[8];
+        load8(p, v);
+        uint4 u;
+        u.x = pack_bf16x2((v[0] - m) * rs * g[0] + be[0], (v[1] - m) * rs * g[1] + be[1]);
+        u.y = pack_bf16x2((v[2] - m) * rs * g[2] + be[2], (v[3] - m) * rs * g[3] + be[3]);
+        u.z = pack_bf16x2((v[4] - m) * rs * g[4] + be[4], (v[5] - m) * rs * g[5] + be[5]);
+        u.w = pack_bf16x2((v[6] - m) * rs * g[6] + be[6], (v[7] - m) * rs * g[7] + be[7]);
+        __nv_bfloat16* orow = out + (((long)b * H + ty0 + p / kTW) * W + tx0 + p % kTW) * C + c_base + o * 8;
+        *reinterpret_cast<uint4*>(orow) = u;
+      }
+    }
+    // peers may still be reading this CTA's partial statistics; also fences stash / statistics reuse
+    cluster.sync();
   }
-  // peers may still be reading this CTA's partial sums
-  if (cluster_size > 1) cluster.sync();
 }
 
-template <typename InT, int CS>
+template <int CS>
 int launch_cluster(const void* x, const float* wgt, const float* bias, const float* gamma, const float* beta,
                    void* out, int B, int H, int W, int C, float eps, cudaStream_t stream) {
   using Cfg = DwCfg<CS>;
-  auto kernel = dwconv7_ln_cluster_kernel<InT, CS>;
+  auto kernel = dwconv7_ln_cluster_kernel<CS>;
   const int cl = C / CS;
   static bool attr_set = false;
+  static int max_clusters[17] = {0};
   if (!attr_set) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set = true;
   }
   const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
+  const long n_tiles = (long)B * tiles_x * tiles_y;
+
+  CUtensorMap tmap;
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+  const uint32_t box[4] = {(uint32_t)CS, (uint32_t)kHW, (uint32_t)kHH, 1u};
+  int rc = make_tmap(&tmap, x, kF32, 4, dims, strides, box, "dwconv7_ln input", /*swizzle_128b=*/false);
+  if (rc != kOk) return rc;
+
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)((long)B * tiles_x * tiles_y * cl));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
@@ -240,8 +256,17 @@ int launch_cluster(const void* x, const float* wgt, const float* bias, const flo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TFIMM_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, reinterpret_cast<const InT*>(x), wgt, bias, gamma, beta,
-                                   reinterpret_cast<__nv_bfloat16*>(out), H, W, C, tiles_x, tiles_x * tiles_y, cl, eps));
+  if (max_clusters[cl] == 0) {
+    cfg.gridDim = dim3((unsigned)(cl * 64));
+    int n = 0;
+    TFIMM_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+    if (n <= 0) return kUnsupported;  // this cluster size cannot be co-scheduled on the device
+    max_clusters[cl] = n;
+  }
+  const long n_clusters = n_tiles < max_clusters[cl] ? n_tiles : max_clusters[cl];
+  cfg.gridDim = dim3((unsigned)(n_clusters * cl));
+  TFIMM_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tmap, wgt, bias, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out),
+                                   H, W, C, tiles_x, tiles_x * tiles_y, (int)n_tiles, cl, eps));
   return kOk;
 }
 
@@ -252,21 +277,10 @@ int launch_cluster(const void* x, const float* wgt, const float* bias, const flo
 int dwconv7_ln_cluster(const void* x, int in_dtype, const float* wgt, const float* bias, const float* gamma,
                        const float* beta, void* out, int out_dtype, int B, int H, int W, int C, float eps,
                        cudaStream_t stream) {
-  if (out_dtype != kBF16) return kUnsupported;
-  int cs = 0;
-  for (int cand : {128, 96}) {
-    if (C % cand == 0) {
-      const int cl = C / cand;
-      if (cl == 1 || cl == 2 || cl == 4 || cl == 8) { cs = cand; break; }
-    }
-  }
-  if (cs == 0) return kUnsupported;
-#define TFIMM_DWC(IN)                                                                                 \
-  return cs == 128 ? launch_cluster<IN, 128>(x, wgt, bias, gamma, beta, out, B, H, W, C, eps, stream)  \
-                   : launch_cluster<IN, 96>(x, wgt, bias, gamma, beta, out, B, H, W, C, eps, stream)
-  if (in_dtype == kF32) { TFIMM_DWC(float); }
-  if (in_dtype == kBF16) { TFIMM_DWC(__nv_bfloat16); }
-#undef TFIMM_DWC
+  if (out_dtype != kBF16 || in_dtype != kF32) return kUnsupported;
+  if ((long)B * H * W * C >= (1L << 40) || (reinterpret_cast<uintptr_t>(x) & 15u) != 0) return kUnsupported;
+  if (C % 64 == 0 && C / 64 <= 16) return launch_cluster<64>(x, wgt, bias, gamma, beta, out, B, H, W, C, eps, stream);
+  if (C % 32 == 0 && C / 32 <= 16) return launch_cluster<32>(x, wgt, bias, gamma, beta, out, B, H, W, C, eps, stream);
   return kUnsupported;
 }
 

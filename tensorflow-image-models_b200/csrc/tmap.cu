@@ -24,9 +24,9 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 }  // namespace
 
-// Generic tiled map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..rank-1.
+// Generic tiled map, SWIZZLE_128B (or none), zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..rank-1.
 int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
+              const uint64_t* strides_bytes, const uint32_t* box, const char* what, bool swizzle_128b) {
   auto encode = get_encode_fn();
   if (encode == nullptr) {
     set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -54,7 +54,8 @@ int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint
   }
   CUresult r = encode(map, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                       (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, bx, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      swizzle_128b ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);

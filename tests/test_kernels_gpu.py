@@ -267,8 +267,17 @@ def test_assemble_tokens():
 @pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.bfloat16), (torch.float32, torch.float32),
                                                 (torch.bfloat16, torch.bfloat16)])
 def test_dwconv7x7_ln(C, H, W, in_dtype, out_dtype):
+    _check_dwconv7x7_ln(C, H, W, in_dtype, out_dtype, B=2)
+
+
+@pytest.mark.parametrize("C,H,W,B", [(512, 14, 14, 48), (1024, 7, 7, 64), (128, 28, 28, 24), (96, 14, 14, 40)])
+def test_dwconv7x7_ln_many_tiles(C, H, W, B):
+    # more tiles than co-resident clusters: the persistent clusters loop, re-using halo / stash / mbarrier phases
+    _check_dwconv7x7_ln(C, H, W, torch.float32, torch.bfloat16, B=B)
+
+
+def _check_dwconv7x7_ln(C, H, W, in_dtype, out_dtype, B):
     ops = _ops()
-    B = 2
     g = torch.Generator(device="cuda").manual_seed(C + H)
     x = torch.randn(B, H, W, C, device="cuda", generator=g).to(in_dtype)
     wgt = torch.randn(49, C, device="cuda", generator=g) / 7
