@@ -14,12 +14,14 @@
 //        and computes a 2-row x 7-column output block: every 8-byte shared-memory load (one halo pixel, two
 //        channels, already fp32x2) feeds up to 14 FFMA2; 686 FFMA2 per 104 loads.  Results (+bias) go to an
 //        fp16 stash [98][CS] in shared memory (11-bit mantissa: 8x finer than the bf16 output)
-//        -> the halo buffer is free again: the TMA copy of the cluster's NEXT tile is issued here and overlaps C/D
+//        -> the halo buffer is free again: the TMA copy of the cluster's NEXT tile is issued here
 //     C. LayerNorm statistics: per-pixel (sum, centred second moment) of the slab, exchanged between the CTAs
 //        of the cluster through distributed shared memory and merged with the parallel-variance formula
 //     D. normalise the own slab and write bf16 rows (16 B per lane)
-// ~81 KB of shared memory and 224 threads per CTA: two CTAs per SM, so one CTA's FMA phase overlaps the
-// other's statistics / store phases.
+// The tile loop is software-pipelined: the cluster barrier is split (arrive after C of tile i, wait after the
+// FMA phase B of tile i+1), so the DSMEM exchange latency hides behind FMA work; stash and partial statistics
+// are double-buffered for that.  ~94 KB of shared memory and 224 threads per CTA: two CTAs per SM, so one CTA's
+// FMA phase also overlaps the other's statistics / store phases.
 #include "common.cuh"
 
 #include <cooperative_groups.h>
@@ -44,10 +46,17 @@ struct DwCfg {
   static constexpr int kOct = CS / 8;                    // 8-channel groups per pixel row
   static constexpr int kPixPerWarp = 32 / kOct;          // pixels per warp step in phases C/D
   static constexpr int kHaloBytes = kHH * kHW * CS * 4;  // fp32
-  static constexpr int kStashBytes = kPix * CS * 2;      // fp16
-  static constexpr int kStatBytes = kPix * 4 * 4;        // part_sum, part_m2, mean, rstd
-  static constexpr int kSmemBytes = kHaloBytes + kStashBytes + kStatBytes + 16;
+  static constexpr int kStashBytes = kPix * CS * 2;      // fp16, per buffer (two buffers)
+  static constexpr int kStatBytes = kPix * 4 * 6;        // 2 x (part_sum, part_m2), mean, rstd
+  static constexpr int kSmemBytes = kHaloBytes + 2 * kStashBytes + kStatBytes + 16;
 };
+
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 template <int CS>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -58,10 +67,9 @@ dwconv7_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const floa
   using Cfg = DwCfg<CS>;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint64_t* halo = reinterpret_cast<const uint64_t*>(smem);                 // [20*13][CS/2] fp32x2
-  __half* stash = reinterpret_cast<__half*>(smem + Cfg::kHaloBytes);              // [98][CS] fp16
-  float* part_sum = reinterpret_cast<float*>(smem + Cfg::kHaloBytes + Cfg::kStashBytes);
-  float* part_m2 = part_sum + kPix;
-  float* s_mean = part_m2 + kPix;
+  __half* stash_base = reinterpret_cast<__half*>(smem + Cfg::kHaloBytes);         // 2 x [98][CS] fp16
+  float* part_base = reinterpret_cast<float*>(smem + Cfg::kHaloBytes + 2 * Cfg::kStashBytes);  // 2 x (sum, m2)[98]
+  float* s_mean = part_base + 4 * kPix;
   float* s_rstd = s_mean + kPix;
   const uint32_t bar = smem_u32(s_rstd + kPix);
   const uint32_t halo_addr = smem_u32(smem);
@@ -97,13 +105,104 @@ dwconv7_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const floa
 
   const int q = lane / Cfg::kOct, o = lane % Cfg::kOct;  // phases C/D: pixel slot / channel octet of this lane
   const float inv_c = 1.0f / (float)C;
-  uint32_t phase = 0;
 
-  for (; tile < n_tiles; tile += n_clusters) {
-    const int b = tile / tiles_per_img, t_in_img = tile % tiles_per_img;
+  auto load8 = [&](const __half* stash, int p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(stash + (size_t)p * CS + o * 8);
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uu[j]));
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  };
+  auto oct_sum = [&](float s) {
+#pragma unroll
+    for (int off = 1; off < Cfg::kOct; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    return s;
+  };
+
+  // ---- C. slab statistics per pixel: sum and second moment about the slab mean ----
+  auto slab_stats = [&](int t, int buf) {
+    const int t_in_img = t % tiles_per_img;
     const int ty0 = (t_in_img / tiles_x) * kTH, tx0 = (t_in_img % tiles_x) * kTW;
-    mbar_wait(bar, phase);
-    phase ^= 1;
+    const __half* stash = stash_base + (size_t)buf * kPix * CS;
+    float* part_sum = part_base + buf * 2 * kPix;
+    float* part_m2 = part_sum + kPix;
+    for (int p0 = warp * Cfg::kPixPerWarp; p0 < kPix; p0 += kWarps * Cfg::kPixPerWarp) {
+      const int p = p0 + q;
+      const bool ok = p < kPix && (ty0 + p / kTW) < H && (tx0 + p % kTW) < W;
+      float v[8];
+      if (ok) load8(stash, p, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+      const float s = oct_sum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])));
+      const float m = s * (1.0f / CS);
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d += (v[j] - m) * (v[j] - m);
+      d = oct_sum(d);
+      if (o == 0 && p < kPix) {
+        part_sum[p] = s;
+        part_m2[p] = ok ? d : 0.f;
+      }
+    }
+  };
+
+  // ---- merge the slabs of the cluster, then D. normalise the own slab and write ----
+  auto finish_tile = [&](int t, int buf) {
+    const int b = t / tiles_per_img, t_in_img = t % tiles_per_img;
+    const int ty0 = (t_in_img / tiles_x) * kTH, tx0 = (t_in_img % tiles_x) * kTW;
+    const __half* stash = stash_base + (size_t)buf * kPix * CS;
+    float* part_sum = part_base + buf * 2 * kPix;
+    float* part_m2 = part_sum + kPix;
+    // Chan et al.: M2 = sum_r [ M2_r + CS * (mean_r - mean)^2 ]
+    for (int p = tid; p < kPix; p += kThreads) {
+      float s = 0.f;
+      for (int r = 0; r < cluster_size; ++r) s += cluster.map_shared_rank(part_sum, r)[p];
+      const float mean = s * inv_c;
+      float m2 = 0.f;
+      for (int r = 0; r < cluster_size; ++r) {
+        const float dm = cluster.map_shared_rank(part_sum, r)[p] * (1.0f / CS) - mean;
+        m2 += cluster.map_shared_rank(part_m2, r)[p] + (float)CS * dm * dm;
+      }
+      s_mean[p] = mean;
+      s_rstd[p] = rsqrtf(m2 * inv_c + eps);
+    }
+    __syncthreads();
+    float g[8], be[8];
+    *reinterpret_cast<float4*>(&g[0]) = __ldg(reinterpret_cast<const float4*>(gamma + c_base + o * 8));
+    *reinterpret_cast<float4*>(&g[4]) = __ldg(reinterpret_cast<const float4*>(gamma + c_base + o * 8 + 4));
+    *reinterpret_cast<float4*>(&be[0]) = __ldg(reinterpret_cast<const float4*>(beta + c_base + o * 8));
+    *reinterpret_cast<float4*>(&be[4]) = __ldg(reinterpret_cast<const float4*>(beta + c_base + o * 8 + 4));
+    for (int p0 = warp * Cfg::kPixPerWarp; p0 < kPix; p0 += kWarps * Cfg::kPixPerWarp) {
+      const int p = p0 + q;
+      if (!(p < kPix && (ty0 + p / kTW) < H && (tx0 + p % kTW) < W)) continue;
+      const float rs = s_rstd[p], mrs = -s_mean[p] * rs;
+      float v[8];
+      load8(stash, p, v);
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaf(fmaf(v[j], rs, mrs), g[j], be[j]);
+      uint4 u;
+      u.x = pack_bf16x2(y[0], y[1]);
+      u.y = pack_bf16x2(y[2], y[3]);
+      u.z = pack_bf16x2(y[4], y[5]);
+      u.w = pack_bf16x2(y[6], y[7]);
+      __nv_bfloat16* orow = out + (((long)b * H + ty0 + p / kTW) * W + tx0 + p % kTW) * C + c_base + o * 8;
+      *reinterpret_cast<uint4*>(orow) = u;
+    }
+  };
+
+  int it = 0, prev_tile = -1;
+  for (; tile < n_tiles; tile += n_clusters, ++it) {
+    const int buf = it & 1;
+    const int ty0 = ((tile % tiles_per_img) / tiles_x) * kTH;
+    mbar_wait(bar, (uint32_t)(it & 1));
+    // every thread is past D of tile it-1 (same stash parity as it+1) and C of tile it-2 before B writes
+    __syncthreads();
 
     // ---- B. depthwise 7x7: warp = output row pair, lane = channel pair ----
     const int oy0 = 2 * warp;
@@ -127,7 +226,8 @@ dwconv7_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const floa
           }
         }
       }
-      __half2* st0 = reinterpret_cast<__half2*>(stash) + (size_t)(oy0 * kTW) * Cfg::kPairs + lane;
+      __half2* st0 =
+          reinterpret_cast<__half2*>(stash_base + (size_t)buf * kPix * CS) + (size_t)(oy0 * kTW) * Cfg::kPairs + lane;
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
         float a0, a1;
@@ -141,85 +241,20 @@ dwconv7_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const floa
     // halo buffer is free: fetch the next tile of this cluster while the statistics / store phases run
     if (tid == 0 && tile + n_clusters < n_tiles) issue_halo(tile + n_clusters);
 
-    auto pixel_valid = [&](int p) { return p < kPix && (ty0 + p / kTW) < H && (tx0 + p % kTW) < W; };
-    auto load8 = [&](int p, float (&v)[8]) {
-      const uint4 u = *reinterpret_cast<const uint4*>(stash + (size_t)p * CS + o * 8);
-      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uu[j]));
-        v[2 * j] = f.x;
-        v[2 * j + 1] = f.y;
-      }
-    };
-    auto oct_sum = [&](float s) {
-#pragma unroll
-      for (int off = 1; off < Cfg::kOct; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-      return s;
-    };
-
-    // ---- C. slab statistics per pixel: sum and second moment about the slab mean ----
-    for (int p0 = warp * Cfg::kPixPerWarp; p0 < kPix; p0 += kWarps * Cfg::kPixPerWarp) {
-      const int p = p0 + q;
-      float v[8];
-      const bool ok = pixel_valid(p);
-      if (ok) load8(p, v);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      }
-      const float s = oct_sum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])));
-      const float m = s * (1.0f / CS);
-      float d = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d += (v[j] - m) * (v[j] - m);
-      d = oct_sum(d);
-      if (o == 0 && p < kPix) {
-        part_sum[p] = s;
-        part_m2[p] = ok ? d : 0.f;
-      }
+    if (prev_tile >= 0) {
+      cluster_wait_acquire();  // partial statistics of the previous tile are visible cluster-wide
+      finish_tile(prev_tile, buf ^ 1);
     }
-    cluster.sync();
-    // merge the slabs (Chan et al.): M2 = sum_r [ M2_r + CS * (mean_r - mean)^2 ]
-    for (int p = tid; p < kPix; p += kThreads) {
-      float s = 0.f;
-      for (int r = 0; r < cluster_size; ++r) s += cluster.map_shared_rank(part_sum, r)[p];
-      const float mean = s * inv_c;
-      float m2 = 0.f;
-      for (int r = 0; r < cluster_size; ++r) {
-        const float dm = cluster.map_shared_rank(part_sum, r)[p] * (1.0f / CS) - mean;
-        m2 += cluster.map_shared_rank(part_m2, r)[p] + (float)CS * dm * dm;
-      }
-      s_mean[p] = mean;
-      s_rstd[p] = rsqrtf(m2 * inv_c + eps);
-    }
-    __syncthreads();
-
-    // ---- D. normalise the own slab and write (8 channels = 16 B per lane) ----
-    {
-      float g[8], be[8];
-      *reinterpret_cast<float4*>(&g[0]) = __ldg(reinterpret_cast<const float4*>(gamma + c_base + o * 8));
-      *reinterpret_cast<float4*>(&g[4]) = __ldg(reinterpret_cast<const float4*>(gamma + c_base + o * 8 + 4));
-      *reinterpret_cast<float4*>(&be[0]) = __ldg(reinterpret_cast<const float4*>(beta + c_base + o * 8));
-      *reinterpret_cast<float4*>(&be[4]) = __ldg(reinterpret_cast<const float4*>(beta + c_base + o * 8 + 4));
-      for (int p0 = warp * Cfg::kPixPerWarp; p0 < kPix; p0 += kWarps * Cfg::kPixPerWarp) {
-        const int p = p0 + q;
-        if (!pixel_valid(p)) continue;
-        const float m = s_mean[p], rs = s_rstd[p];
-        float v[8];
-        load8(p, v);
-        uint4 u;
-        u.x = pack_bf16x2((v[0] - m) * rs * g[0] + be[0], (v[1] - m) * rs * g[1] + be[1]);
-        u.y = pack_bf16x2((v[2] - m) * rs * g[2] + be[2], (v[3] - m) * rs * g[3] + be[3]);
-        u.z = pack_bf16x2((v[4] - m) * rs * g[4] + be[4], (v[5] - m) * rs * g[5] + be[5]);
-        u.w = pack_bf16x2((v[6] - m) * rs * g[6] + be[6], (v[7] - m) * rs * g[7] + be[7]);
-        __nv_bfloat16* orow = out + (((long)b * H + ty0 + p / kTW) * W + tx0 + p % kTW) * C + c_base + o * 8;
-        *reinterpret_cast<uint4*>(orow) = u;
-      }
-    }
-    // peers may still be reading this CTA's partial statistics; also fences stash / statistics reuse
-    cluster.sync();
+    slab_stats(tile, buf);
+    cluster_arrive_release();
+    prev_tile = tile;
   }
+  if (prev_tile >= 0) {
+    cluster_wait_acquire();
+    finish_tile(prev_tile, (it - 1) & 1);
+  }
+  // a CTA must not exit while peers may still read its partial statistics through DSMEM
+  cluster.sync();
 }
 
 template <int CS>
