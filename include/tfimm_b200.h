@@ -57,7 +57,8 @@ int tfimm_b200_sm_count(void);
  * tfimm/layers/transformers.py:192-205, the classifier heads (vit.py:364-368, swin.py:457-461,
  * convnext.py:356-360, efficientnet.py:259-263) and 1x1 Conv2D (efficientnet_blocks.py:412-434,
  * resnet.py:220-248); gamma/residual fuse ConvNeXtBlock's layer-scale + shortcut (convnext.py:226-227).
- * force_block_n: 0 = auto, else 64/128/256 (testing). */
+ * force_block_n: 0 = auto; 64/128/256 = one-CTA kernel with that tile width; 2 = CTA-pair (cta_group::2)
+ * 256x256 kernel (testing / A-B measurements). */
 int tfimm_b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias,
                          const float* gamma, const void* residual, int ldr, void* C, int ldc, int M, int N,
                          int K, int act, int act_after_residual, int out_dtype, int force_block_n, void* stream);

@@ -51,13 +51,6 @@ struct DwCfg {
   static constexpr int kSmemBytes = kHaloBytes + 2 * kStashBytes + kStatBytes + 16;
 };
 
-__device__ __forceinline__ void cluster_arrive_release() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void cluster_wait_acquire() {
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 template <int CS>
 __global__ void __launch_bounds__(kThreads, 2)
 dwconv7_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ wgt /*[49][C]*/,

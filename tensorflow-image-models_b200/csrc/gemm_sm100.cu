@@ -18,9 +18,14 @@
 //               -> TMA store.  Each warp owns its 32-row slab, so there is no cross-warp barrier;
 //               the residual chunk is TMA-prefetched into the same slab while the accumulator is
 //               being loaded and activated, and may alias the output (in-place residual stream).
-#include "common.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace tfimm {
+
+int gemm_bf16_pair(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
+                   const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act, int act_post,
+                   int out_dtype, cudaStream_t stream);
+
 namespace {
 
 constexpr int kBlockM = 128;
@@ -28,7 +33,7 @@ constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kNumEpiWarps = 8;
 constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
-constexpr int kSlabBytes = 32 * 128;  // 32 rows x 128 B, one per epilogue warp
+constexpr int kSlabBytes = kEpiSlabBytes;
 constexpr int kAccStages = 2;
 
 template <int BLOCK_N>
@@ -43,65 +48,6 @@ struct GemmCfg {
       kStages * kStageBytes + kSlabTotal + kNumBarriers * 8 + 16 + 1024 /*alignment slack*/;
   static constexpr uint32_t kTmemCols = kAccStages * BLOCK_N;  // 512 / 256 / 128
 };
-
-struct GemmParams {
-  int M, N, K;
-  const float* bias;   // [N] or null
-  const float* gamma;  // [N] or null
-  int act;
-  int has_res;
-  int act_post;  // 1: activation applied after the residual add (ResNet: act(x + shortcut))
-};
-
-// v[j] (+ or *)= vec[n0 + j] on packed pairs; full chunks use 16-byte loads.
-template <int CH, bool kMul>
-__device__ __forceinline__ void apply_vec(uint64_t (&v)[CH / 2], const float* __restrict__ vec, int n0, int N) {
-  if (n0 + CH <= N) {
-#pragma unroll
-    for (int j = 0; j < CH; j += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(vec + n0 + j));
-      if (kMul) {
-        v[j / 2] = mul2(v[j / 2], pack2(b4.x, b4.y));
-        v[j / 2 + 1] = mul2(v[j / 2 + 1], pack2(b4.z, b4.w));
-      } else {
-        v[j / 2] = add2(v[j / 2], pack2(b4.x, b4.y));
-        v[j / 2 + 1] = add2(v[j / 2 + 1], pack2(b4.z, b4.w));
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < CH; j += 2) {
-      const float neutral = kMul ? 1.f : 0.f;
-      const float b0 = (n0 + j < N) ? __ldg(vec + n0 + j) : neutral;
-      const float b1 = (n0 + j + 1 < N) ? __ldg(vec + n0 + j + 1) : neutral;
-      v[j / 2] = kMul ? mul2(v[j / 2], pack2(b0, b1)) : add2(v[j / 2], pack2(b0, b1));
-    }
-  }
-}
-
-template <int NP>
-__device__ __forceinline__ void apply_act_pairs(uint64_t (&v)[NP], int act) {
-  switch (act) {
-    case kActGelu:
-#pragma unroll
-      for (int j = 0; j < NP; ++j) v[j] = gelu_fast2(v[j]);
-      break;
-    case kActSwish:
-#pragma unroll
-      for (int j = 0; j < NP; ++j) v[j] = swish_fast2(v[j]);
-      break;
-    case kActNone:
-      break;
-    default:
-#pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        float a, b;
-        unpack2(v[j], a, b);
-        v[j] = pack2(apply_act<false>(a, act), apply_act<false>(b, act));
-      }
-      break;
-  }
-}
 
 template <int BLOCK_N, typename OutT>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -217,7 +163,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int grp = ew >> 2;             // which half of the column chunks this warp takes
     const uint32_t slab = smem_slabs + (uint32_t)ew * kSlabBytes;
     uint8_t* my_row = smem_gen + (slab - smem_base) + lane * 128;
-    const int sw = lane & 7;             // TMA SWIZZLE_128B: 16-byte chunk j of row r lives at j ^ (r & 7)
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t cc = 0;  // chunks processed by this warp (residual barrier parity)
@@ -237,85 +182,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll 1
       for (int c = grp; c < nvalid; c += 2) {
         const int n0 = n_blk * BLOCK_N + c * CH;
-        // the previous store of this warp must have finished reading the slab
-        if (lane == 0) {
-          tma_store_wait_read<0>();
-          if (p.has_res) {
-            mbar_expect_tx(res_bar(ew), kSlabBytes);
-            tma_load_2d(slab, &tmap_r, res_bar(ew), n0, row0);
-          }
-        }
-        __syncwarp();
-        uint64_t v[CH / 2];
-        {
-          uint32_t r[32];
-#pragma unroll
-          for (int h = 0; h < CH / 32; ++h) {
-            tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * CH + h * 32), r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              v[h * 16 + j] = pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-          }
-        }
-        if (c + 2 >= nvalid) {
-          // all TMEM reads of this accumulator stage by this warp are done
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
-        if (p.bias != nullptr) apply_vec<CH, false>(v, p.bias, n0, p.N);
-        if (!p.act_post) apply_act_pairs(v, p.act);
-        if (p.gamma != nullptr) apply_vec<CH, true>(v, p.gamma, n0, p.N);
-        if (p.has_res) {
-          mbar_wait(res_bar(ew), cc & 1u);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
-            if constexpr (sizeof(OutT) == 2) {
-              const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
-              const float2 f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-              v[4 * j + 0] = add2(v[4 * j + 0], pack2(f0.x, f0.y));
-              v[4 * j + 1] = add2(v[4 * j + 1], pack2(f1.x, f1.y));
-              v[4 * j + 2] = add2(v[4 * j + 2], pack2(f2.x, f2.y));
-              v[4 * j + 3] = add2(v[4 * j + 3], pack2(f3.x, f3.y));
-            } else {
-              v[2 * j + 0] = add2(v[2 * j + 0], pack2(__uint_as_float(u.x), __uint_as_float(u.y)));
-              v[2 * j + 1] = add2(v[2 * j + 1], pack2(__uint_as_float(u.z), __uint_as_float(u.w)));
-            }
-          }
-        }
-        if (p.act_post) apply_act_pairs(v, p.act);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 u;
-          if constexpr (sizeof(OutT) == 2) {
-            float a0, a1, a2, a3, a4, a5, a6, a7;
-            unpack2(v[4 * j + 0], a0, a1);
-            unpack2(v[4 * j + 1], a2, a3);
-            unpack2(v[4 * j + 2], a4, a5);
-            unpack2(v[4 * j + 3], a6, a7);
-            u.x = pack_bf16x2(a0, a1);
-            u.y = pack_bf16x2(a2, a3);
-            u.z = pack_bf16x2(a4, a5);
-            u.w = pack_bf16x2(a6, a7);
-          } else {
-            float a0, a1, a2, a3;
-            unpack2(v[2 * j + 0], a0, a1);
-            unpack2(v[2 * j + 1], a2, a3);
-            u.x = __float_as_uint(a0);
-            u.y = __float_as_uint(a1);
-            u.z = __float_as_uint(a2);
-            u.w = __float_as_uint(a3);
-          }
-          *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = u;
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmap_c, slab, n0, row0);
-          tma_store_commit();
-        }
+        const bool last = c + 2 >= nvalid;
+        epilogue_chunk<OutT>(p, t_acc + (uint32_t)(c * CH), n0, row0, slab, my_row, lane, res_bar(ew), cc & 1u,
+                             &tmap_c, &tmap_r, [&]() {
+                               if (last) {
+                                 // all TMEM reads of this accumulator stage by this warp are done
+                                 tcgen05_fence_before();
+                                 __syncwarp();
+                                 if (lane == 0) mbar_arrive(tempty_bar(acc));
+                               }
+                             });
         ++cc;
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
@@ -379,6 +255,26 @@ int pick_block_n(int M, int N) {
   return best;
 }
 
+// CTA-pair kernel (gemm2_sm100.cu) when its 256 x 256 tiles fill the machine at least as well as the best
+// one-CTA tiling: cost = waves x tile width, the pair kernel's MMA rate per SM being ~15% higher.
+bool prefer_pair(int M, int N) {
+  static const int mode = [] {
+    const char* e = getenv("TFIMM_B200_GEMM");  // "1cta" / "2cta" force one kernel (A/B measurements)
+    return e == nullptr ? 0 : (e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0));
+  }();
+  if (mode == 1) return false;
+  if (mode == 2) return true;
+  if (N < 256 || M < 256) return false;
+  const int sms = sm_count();
+  const long tiles2 = (long)((M + 255) / 256) * ((N + 255) / 256);
+  const long waves2 = (tiles2 + sms / 2 - 1) / (sms / 2);
+  const double cost2 = (double)waves2 * 256 * 0.87;
+  const int bn = pick_block_n(M, N);
+  const long tiles1 = (long)((M + kBlockM - 1) / kBlockM) * ((N + bn - 1) / bn);
+  const double cost1 = (double)((tiles1 + sms - 1) / sms) * bn * (bn == 256 ? 1.0 : (bn == 128 ? 1.04 : 1.10));
+  return cost2 <= cost1;
+}
+
 }  // namespace
 
 int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const float* bias,
@@ -390,6 +286,11 @@ int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const flo
   TFIMM_CHECK_ARG(K % 8 == 0, "gemm: K must be a multiple of 8 (got %d)", K);
   TFIMM_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0, "gemm: bias must be 16-byte aligned");
   TFIMM_CHECK_ARG(gamma == nullptr || (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0, "gemm: gamma must be 16-byte aligned");
+  // force_block_n: 0 = choose; 64/128/256 = one-CTA kernel with that tile width; 2 = CTA-pair 256x256 kernel
+  if (force_block_n == 2 || (force_block_n == 0 && prefer_pair(M, N))) {
+    return gemm_bf16_pair(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act, act_post, out_dtype,
+                          stream);
+  }
   const int bn = force_block_n > 0 ? force_block_n : pick_block_n(M, N);
 #define TFIMM_GEMM_CASE(BN)                                                                           \
   case BN:                                                                                            \

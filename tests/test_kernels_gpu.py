@@ -68,7 +68,27 @@ def test_gemm_bf16_plain(M, N, K, out_dtype):
     assert err < tol, (err, tol)
 
 
-@pytest.mark.parametrize("block_n", [64, 128, 256])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 768, 768), (394, 2304, 768), (1000, 1000, 1024),
+                                   (50432 // 4, 768, 3072), (300, 384, 128), (77, 1000, 192), (4736, 3072, 768)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_bf16_cta_pair(M, N, K, out_dtype):
+    """block_n=2 forces the cta_group::2 kernel (256x256 tiles over two SMs): M/N tails, many tiles per pair
+    (accumulator-stage and smem-ring wrap-around), residual in place."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g).to(out_dtype)
+    ref = x.float() + torch.nn.functional.gelu(a.float() @ w.float().t() + bias)
+    ops.gemm(a, w, bias=bias, act="gelu", residual=x, out=x, block_n=2)
+    torch.cuda.synchronize()
+    err = (x.float() - ref).abs().max().item()
+    tol = 3e-3 if out_dtype == torch.float32 else 2e-2 + 4e-3 * ref.abs().max().item()
+    assert err < tol, (err, tol)
+
+
+@pytest.mark.parametrize("block_n", [64, 128, 256, 2])
 @pytest.mark.parametrize("act", [None, "gelu", "swish", "relu", "relu6", "tanh", "sigmoid"])
 def test_gemm_bf16_epilogues(block_n, act):
     ops = _ops()

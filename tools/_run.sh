@@ -1,5 +1,10 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "dwconv7x7" 2>&1 | tail -8
-python tools/prof_kernels.py dwconv_ln 2>&1 | tail -1
-timeout 600 python bench.py --model convnext_base --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_convnext_base.json 2> gpurun_out/bench_convnext_base.err
-tail -3 gpurun_out/bench_convnext_base.err; cut -c1-300 gpurun_out/bench_convnext_base.json
+for mode in 1cta auto; do
+for m in vit_base_patch16_224 swin_base_patch4_window7_224 convnext_base; do
+  TFIMM_B200_GEMM=$mode timeout 600 python bench.py --model $m --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_${m}_$mode.json 2> gpurun_out/bench_${m}_$mode.err
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_${m}_$mode.json").read().strip().splitlines()[-1])
+print("$mode $m", round(d["value"]), round(d["ms_per_step"],2), d["roofline"]["families_ms"], d["clocks"])
+PY
+done; done
