@@ -63,6 +63,28 @@ int tfimm_b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, const f
                          const float* gamma, const void* residual, int ldr, void* C, int ldc, int M, int N,
                          int K, int act, int act_after_residual, int out_dtype, int force_block_n, void* stream);
 
+/* LayerNorm folded into the dense layer that follows it (tf.keras.layers.LayerNormalization -> Dense at
+ * tfimm/architectures/vit.py:240-262, swin.py:262-300, convnext.py:197-226): same contraction as
+ * tfimm_b200_gemm_bf16 with two optional extras.
+ *   consumer side (ln_stats != NULL): A holds the RAW rows x in bf16, W = bf16(gamma_ln * W), bias already
+ *     contains W beta_ln, ln_colsum[n] = sum_k W[n][k]; per-row mean/rstd are rebuilt from ln_parts partial
+ *     (sum, sum of squares) pairs per row, ln_stats[M][ln_parts][2], and applied in the epilogue:
+ *     LN(x) W^T = rstd * (x W^T - mean * colsum).  The normalised dimension is K.
+ *   producer side (emit_stats != NULL): besides C, writes this GEMM's per-row partial statistics
+ *     emit_stats[M][emit_parts][2] (emit_parts must equal tfimm_b200_gemm_stat_parts(M, N, force_block_n)) and,
+ *     if emit_bf16 != NULL (fp32 C only), a bf16 copy of C, the A operand of the next folded GEMM.
+ * This removes the standalone LayerNorm pass over the fp32 residual stream. */
+int tfimm_b200_gemm_bf16_ln(const void* A, int lda, const void* W, int ldw, const float* bias,
+                            const float* gamma, const void* residual, int ldr, void* C, int ldc, int M, int N,
+                            int K, int act, int act_after_residual, int out_dtype, int force_block_n,
+                            const float* ln_stats, int ln_parts, const float* ln_colsum, float ln_eps,
+                            void* emit_bf16, int ld_emit, float* emit_stats, int emit_parts, void* stream);
+int tfimm_b200_gemm_stat_parts(int M, int N, int force_block_n);
+/* bf16 copy + one (sum, sum of squares) partial per row of an fp32 [rows][C] matrix: entry point of a
+ * LayerNorm-folded stream (after the token assembly / patch embedding, which are not GEMM epilogues). */
+int tfimm_b200_row_stats_cast(const float* x, long in_stride, void* out_bf16, long out_stride, float* stats,
+                              long rows, int C, void* stream);
+
 /* Same contract in fp32 on CUDA cores (precision="fp32" parity mode). */
 int tfimm_b200_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
                         const float* gamma, const float* residual, int ldr, float* C, int ldc, int M, int N,

@@ -65,9 +65,9 @@ int sm_count();
 
 // tmap.cu: TMA descriptors (SWIZZLE_128B, zero OOB fill)
 int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, const char* what, bool swizzle_128b = true);
+              const uint64_t* strides_bytes, const uint32_t* box, const char* what, int swizzle_bytes = 128);
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
-                 uint32_t box_rows, uint32_t box_cols, const char* what);
+                 uint32_t box_rows, uint32_t box_cols, const char* what, int swizzle_bytes = 128);
 
 // ----------------------------------------------------------------------------
 // Small device math
@@ -148,6 +148,24 @@ __device__ __forceinline__ uint64_t gelu_fast2(uint64_t x) {
   const uint64_t h = mul2(mul2(p, e), ax);  // |x| * Phi(-|x|)
   // gelu(x) = relu(x) - h
   return fma2(h, splat2(-1.0f), pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+// GELU (erf form) without MUFU: x * Phi(x), Phi(x) = 1/2 + xc * P(xc^2), xc = clamp(x, -4, 4), P a degree-6
+// minimax fit of (Phi(x) - 1/2) / x on [0, 4] (weighted for the error of x * Phi).  |abs error| < 2e-4 for all x
+// (relative 4e-5 |x| beyond the clamp), i.e. well below one bf16 ulp of the GEMM outputs it is applied to.
+// 9 packed FMA-pipe instructions + 4 FMNMX per PAIR (gelu_fast2: 11 + 4 ALU + 4 MUFU): the epilogue of the
+// K = 768 GEMMs is instruction/MUFU bound (profiles/r01_ncu_full_gemm_fc1.txt), not tensor bound.
+__device__ __forceinline__ uint64_t gelu_poly2(uint64_t x) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  const uint64_t xc = pack2(fminf(fmaxf(x0, -4.0f), 4.0f), fminf(fmaxf(x1, -4.0f), 4.0f));
+  const uint64_t t = mul2(xc, xc);
+  uint64_t p = fma2(splat2(2.27813761e-08f), t, splat2(-1.59859863e-06f));
+  p = fma2(p, t, splat2(4.79554370e-05f));
+  p = fma2(p, t, splat2(-8.14014580e-04f));
+  p = fma2(p, t, splat2(8.77238349e-03f));
+  p = fma2(p, t, splat2(-6.45730991e-02f));
+  p = fma2(p, t, splat2(3.97883340e-01f));
+  return mul2(x, fma2(xc, p, splat2(0.5f)));
 }
 __device__ __forceinline__ uint64_t swish_fast2(uint64_t x) {
   float z0, z1;

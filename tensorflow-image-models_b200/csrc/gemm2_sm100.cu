@@ -28,11 +28,11 @@ constexpr int kUmmaK = 16;
 constexpr int kNumEpiWarps = 8;
 constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
 constexpr int kAccStages = 2;
-constexpr int kStages = 6;
+constexpr int kStages = 5;
 constexpr int kABytes = kCtaM * kBlockK * 2;
 constexpr int kBBytes = kHalfN * kBlockK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;  // per CTA
-constexpr int kSlabTotal = kNumEpiWarps * kEpiSlabBytes;
+constexpr int kSlabTotal = kNumEpiWarps * (kEpiSlabBytes + kEpiCopySlabBytes);  // output slabs, then bf16-copy slabs
 constexpr int kNumBarriers = 2 * kStages + 2 * kAccStages + kNumEpiWarps;
 constexpr int kSmemBytes = kStages * kStageBytes + kSlabTotal + kNumBarriers * 8 + 16 + 1024 /*alignment slack*/;
 constexpr uint32_t kTmemCols = kAccStages * kBlockN;  // 512: all of this SM's tensor memory
@@ -43,7 +43,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                               const __grid_constant__ CUtensorMap tmap_b,
                               const __grid_constant__ CUtensorMap tmap_c,
-                              const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
+                              const __grid_constant__ CUtensorMap tmap_r,
+                              const __grid_constant__ CUtensorMap tmap_c2, const GemmParams p) {
   constexpr int CH = 128 / (int)sizeof(OutT);  // output columns per 128-byte slab row
   constexpr int NCH = kBlockN / CH;
 
@@ -159,6 +160,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int grp = ew >> 2;             // which half of the column chunks this warp takes
     const uint32_t slab = smem_slabs + (uint32_t)ew * kEpiSlabBytes;
     uint8_t* my_row = smem_gen + (slab - smem_base) + lane * 128;
+    const uint32_t copy_slab = smem_slabs + kNumEpiWarps * kEpiSlabBytes + (uint32_t)ew * kEpiCopySlabBytes;
+    uint8_t* copy_row = smem_gen + (copy_slab - smem_base) + lane * 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t cc = 0;  // chunks processed by this warp (residual barrier parity)
@@ -177,14 +180,18 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (lane == 0) mbar_arrive_cluster(tempty_leader);
       };
       if (grp >= nvalid) release_acc();  // nothing to read for this warp in this tile
+      float ln_rstd = 1.f, ln_nmr = 0.f, stat_s = 0.f, stat_q = 0.f;
+      if (p.ln_stats != nullptr) ln_row_coeffs(p, row0 + lane, ln_rstd, ln_nmr);
 #pragma unroll 1
       for (int c = grp; c < nvalid; c += 2) {
         const int n0 = n_blk * kBlockN + c * CH;
         const bool last = c + 2 >= nvalid;
         epilogue_chunk<OutT>(p, t_acc + (uint32_t)(c * CH), n0, row0, slab, my_row, lane, res_bar(ew), cc & 1u,
-                             &tmap_c, &tmap_r, [&]() { if (last) release_acc(); });
+                             &tmap_c, &tmap_r, &tmap_c2, copy_slab, copy_row, ln_rstd, ln_nmr, stat_s, stat_q,
+                             [&]() { if (last) release_acc(); });
         ++cc;
       }
+      if (p.emit_stats != nullptr) emit_row_stats(p, row0 + lane, 2 * n_blk + grp, 2 * num_n_tiles, stat_s, stat_q);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -201,9 +208,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 template <typename OutT>
-int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
-                     const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act, int act_post,
-                     cudaStream_t stream) {
+int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const void* residual, int ldr, void* C, int ldc,
+                     const GemmParams& p, cudaStream_t stream) {
+  const int M = p.M, N = p.N, K = p.K;
   constexpr int out_dtype = sizeof(OutT) == 2 ? kBF16 : kF32;
   constexpr int CH = 128 / (int)sizeof(OutT);
   CUtensorMap ta, tb, tc, tr;
@@ -216,31 +223,30 @@ int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const float
   } else {
     tr = tc;
   }
+  CUtensorMap tc2 = tc;
+  if (p.emit_bf16 != nullptr) {
+    if ((st = make_tmap_2d(&tc2, p.emit_bf16, kBF16, M, N, p.ld_emit, 32, 32, "bf16 copy", 64)) != kOk) return st;
+  }
   auto kernel = gemm_bf16_tcgen05_pair_kernel<OutT>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  GemmParams p{M, N, K, bias, gamma, act, residual != nullptr ? 1 : 0, act_post};
   const int tiles = ((M + kPairM - 1) / kPairM) * ((N + kBlockN - 1) / kBlockN);
   const int max_pairs = sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  kernel<<<2 * pairs, kNumThreads, kSmemBytes, stream>>>(ta, tb, tc, tr, p);
+  kernel<<<2 * pairs, kNumThreads, kSmemBytes, stream>>>(ta, tb, tc, tr, tc2, p);
   TFIMM_LAUNCH_OK("gemm_bf16_tcgen05_pair_kernel");
   return kOk;
 }
 
 }  // namespace
 
-int gemm_bf16_pair(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
-                   const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act, int act_post,
-                   int out_dtype, cudaStream_t stream) {
-  return out_dtype == kBF16
-             ? launch_gemm_pair<__nv_bfloat16>(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act,
-                                               act_post, stream)
-             : launch_gemm_pair<float>(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act, act_post,
-                                       stream);
+int gemm_bf16_pair(const void* A, int lda, const void* W, int ldw, const void* residual, int ldr, void* C, int ldc,
+                   const GemmParams& p, int out_dtype, cudaStream_t stream) {
+  return out_dtype == kBF16 ? launch_gemm_pair<__nv_bfloat16>(A, lda, W, ldw, residual, ldr, C, ldc, p, stream)
+                            : launch_gemm_pair<float>(A, lda, W, ldw, residual, ldr, C, ldc, p, stream);
 }
 
 }  // namespace tfimm

@@ -24,9 +24,9 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 }  // namespace
 
-// Generic tiled map, SWIZZLE_128B (or none), zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..rank-1.
+// Generic tiled map, swizzle_bytes in {128, 64, 0 = none}, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..rank-1.
 int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, const char* what, bool swizzle_128b) {
+              const uint64_t* strides_bytes, const uint32_t* box, const char* what, int swizzle_bytes) {
   auto encode = get_encode_fn();
   if (encode == nullptr) {
     set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -55,7 +55,8 @@ int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint
   CUresult r = encode(map, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                       (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, bx, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      swizzle_128b ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                      : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
@@ -66,12 +67,12 @@ int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint
 
 // 2D row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols].
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
-                 uint32_t box_rows, uint32_t box_cols, const char* what) {
+                 uint32_t box_rows, uint32_t box_cols, const char* what, int swizzle_bytes) {
   const uint64_t esize = dtype == kBF16 ? 2 : 4;
   const uint64_t dims[2] = {cols, rows};
   const uint64_t strides[1] = {ld * esize};
   const uint32_t box[2] = {box_cols, box_rows};
-  return make_tmap(map, ptr, dtype, 2, dims, strides, box, what);
+  return make_tmap(map, ptr, dtype, 2, dims, strides, box, what, swizzle_bytes);
 }
 
 }  // namespace tfimm
