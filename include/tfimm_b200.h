@@ -165,9 +165,23 @@ int tfimm_b200_global_avg_pool(const void* x, int dtype, float* out, int B, int 
 /* im2col for dense k x k convolutions (stems, fused-MBConv / ResNet 3x3, 7x7) that then run as tcgen05
  * GEMMs: out[(b,oy,ox), (ky,kx,c)] = x[b, oy*s+ky-pad_t, ox*s+kx-pad_l, c], zero outside / beyond k*k*C.
  * Replaces the gather half of tf.keras.layers.Conv2D at efficientnet.py:216-222,
- * efficientnet_blocks.py:482-497 (conv_exp), resnet.py:130-137,230-238,506-512. */
-int tfimm_b200_im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int ks,
-                      int stride, int pad_t, int pad_l, int Ho, int Wo, int Kpad, void* stream);
+ * efficientnet_blocks.py:482-497 (conv_exp), resnet.py:130-137,230-238,506-512.
+ * groups > 1 (wide ResNeXt groups, resnet.py:230-238 with cardinality 32 and >= 48 channels per group):
+ * out[g][(b,oy,ox)][(ky,kx,c)] with c < C/groups, i.e. one [M][Kpad] matrix per group, each followed by its own GEMM. */
+int tfimm_b200_im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int groups,
+                      int ks, int stride, int pad_t, int pad_l, int Ho, int Wo, int Kpad, void* stream);
+
+/* GroupNormalization over NHWC (tfimm/layers/norm.py:22-101, norm_layer "group_norm" = 32 groups, eps 1e-5;
+ * used by resnet50_gn in place of every BatchNormalization): moments over (H, W, C/groups) per image and group,
+ * biased variance, per-channel gamma/beta, then optional "+ residual" and activation (resnet.py:284-290).
+ * stats: workspace of B * groups * 2 floats. */
+int tfimm_b200_group_norm(const void* x, int dtype, const float* gamma, const float* beta, const void* residual,
+                          void* out, float* stats, int B, int HW, int C, int groups, float eps, int act, void* stream);
+
+/* BlurPool2D (tfimm/layers/blurpool.py:54-62; resnetblur50: resnet.py:127-140, 218-241, 532-536): REFLECT pad 1,
+ * depthwise [1 2 1] x [1 2 1] / 16, stride s, VALID.  Ho = (H - 1) / s + 1. */
+int tfimm_b200_blur_pool(const void* x, int dtype, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo,
+                         void* stream);
 
 /* SqueezeExcite gate from pooled sums: gate[b] = gate_act(W_e act(W_r mean[b] + b_r) + b_e), fp32.
  * efficientnet_blocks.py:241-247 (mean -> conv_reduce -> act1 -> conv_expand -> gate), layers/attention.py:67-75.

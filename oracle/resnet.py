@@ -17,8 +17,10 @@ def make_divisible(value, divisor, min_value=None, round_limit=0.9):
     return new_value
 
 
-def _bn(s, prefix, ch):
-    for leaf in ("gamma", "beta", "moving_mean", "moving_variance"):
+def _bn(s, prefix, ch, kind="batch_norm"):
+    # GroupNormalization has gamma / beta only, no moving statistics (tfimm/layers/norm.py:143-160)
+    leaves = ("gamma", "beta") if kind.startswith("group_norm") else ("gamma", "beta", "moving_mean", "moving_variance")
+    for leaf in leaves:
         s[f"{prefix}/{leaf}"] = (ch,)
 
 
@@ -51,35 +53,35 @@ def param_shapes(cfg):
     if cfg.stem_type in {"deep", "deep_tiered"}:
         c0 = 3 * (cfg.stem_width // 4) if cfg.stem_type == "deep_tiered" else cfg.stem_width
         s["conv1/0/kernel"] = (3, 3, cfg.in_channels, c0)
-        _bn(s, "conv1/1", c0)
+        _bn(s, "conv1/1", c0, cfg.norm_layer)
         s["conv1/3/kernel"] = (3, 3, c0, cfg.stem_width)
-        _bn(s, "conv1/4", cfg.stem_width)
+        _bn(s, "conv1/4", cfg.stem_width, cfg.norm_layer)
         s["conv1/6/kernel"] = (3, 3, cfg.stem_width, cfg.stem_width * 2)
         stem_out = cfg.stem_width * 2
     else:
         s["conv1/kernel"] = (7, 7, cfg.in_channels, 64)
         stem_out = 64
-    _bn(s, "bn1", stem_out)
+    _bn(s, "bn1", stem_out, cfg.norm_layer)
     if cfg.replace_stem_pool:
         s["maxpool/0/kernel"] = (3, 3, stem_out, stem_out)
-        _bn(s, "maxpool/1", stem_out)
+        _bn(s, "maxpool/1", stem_out, cfg.norm_layer)
     for b in _plan(cfg):
         p, ch, cin, cout = b["name"], b["nb_channels"], b["cin"], b["cout"]
         if cfg.block == "basic_block":
             first = ch // cfg.block_reduce_first
             s[f"{p}/conv1/kernel"] = (3, 3, cin, first)
-            _bn(s, f"{p}/bn1", first)
+            _bn(s, f"{p}/bn1", first, cfg.norm_layer)
             s[f"{p}/conv2/kernel"] = (3, 3, first, cout)
-            _bn(s, f"{p}/bn2", cout)
+            _bn(s, f"{p}/bn2", cout, cfg.norm_layer)
         else:
             width = int(math.floor(ch * (cfg.base_width / 64)) * cfg.cardinality)
             first = width // cfg.block_reduce_first
             s[f"{p}/conv1/kernel"] = (1, 1, cin, first)
-            _bn(s, f"{p}/bn1", first)
+            _bn(s, f"{p}/bn1", first, cfg.norm_layer)
             s[f"{p}/conv2/kernel"] = (3, 3, first // cfg.cardinality, width)
-            _bn(s, f"{p}/bn2", width)
+            _bn(s, f"{p}/bn2", width, cfg.norm_layer)
             s[f"{p}/conv3/kernel"] = (1, 1, width, cout)
-            _bn(s, f"{p}/bn3", cout)
+            _bn(s, f"{p}/bn3", cout, cfg.norm_layer)
         if cfg.attn_layer == "se":
             rd = make_divisible(cout * cfg.se_ratio, 8, round_limit=0.0)
             s[f"{p}/se/fc1/kernel"] = (1, 1, cout, rd)
@@ -91,10 +93,10 @@ def param_shapes(cfg):
         if b["down"]:
             if cfg.downsample_mode == "conv":
                 s[f"{p}/downsample/0/kernel"] = (cfg.down_kernel_size, cfg.down_kernel_size, cin, cout)
-                _bn(s, f"{p}/downsample/1", cout)
+                _bn(s, f"{p}/downsample/1", cout, cfg.norm_layer)
             else:
                 s[f"{p}/downsample/1/kernel"] = (1, 1, cin, cout)
-                _bn(s, f"{p}/downsample/2", cout)
+                _bn(s, f"{p}/downsample/2", cout, cfg.norm_layer)
     if cfg.nb_classes > 0:
         s["remove/fc/kernel"] = (_plan(cfg)[-1]["cout"], cfg.nb_classes)
         s["remove/fc/bias"] = (cfg.nb_classes,)
@@ -131,16 +133,21 @@ def _downsample(x, w, prefix, cfg, stride):
 def block(x, w, b, cfg):
     p, stride, act = b["name"], b["stride"], cfg.act_layer
     shortcut = x
+    use_aa = bool(cfg.aa_layer) and stride == 2  # the blur layer takes over the stride (resnet.py:127-140, 218-241)
     if cfg.block == "basic_block":  # BasicBlock.call, resnet.py:166-189
-        x = tf.conv2d(x, w[f"{p}/conv1/kernel"], stride=stride, padding=1)
+        x = tf.conv2d(x, w[f"{p}/conv1/kernel"], stride=1 if use_aa else stride, padding=1)
         x = tf.act(tf.norm(x, w, f"{p}/bn1", cfg.norm_layer), act)
+        if use_aa:
+            x = tf.blur_pool2d(x, stride)
         x = tf.conv2d(x, w[f"{p}/conv2/kernel"], padding=1)
         x = tf.norm(x, w, f"{p}/bn2", cfg.norm_layer)
     else:  # Bottleneck.call, resnet.py:266-292
         x = tf.conv2d(x, w[f"{p}/conv1/kernel"])
         x = tf.act(tf.norm(x, w, f"{p}/bn1", cfg.norm_layer), act)
-        x = tf.conv2d(x, w[f"{p}/conv2/kernel"], stride=stride, padding=1, groups=cfg.cardinality)
+        x = tf.conv2d(x, w[f"{p}/conv2/kernel"], stride=1 if use_aa else stride, padding=1, groups=cfg.cardinality)
         x = tf.act(tf.norm(x, w, f"{p}/bn2", cfg.norm_layer), act)
+        if use_aa:
+            x = tf.blur_pool2d(x, stride)
         x = tf.conv2d(x, w[f"{p}/conv3/kernel"])
         x = tf.norm(x, w, f"{p}/bn3", cfg.norm_layer)
     x = _attn(x, w, f"{p}/se", cfg)
@@ -167,7 +174,10 @@ def forward_features(cfg, w, x, return_features=False):
         x = tf.act(tf.norm(x, w, "maxpool/1", cfg.norm_layer), act)
     else:
         x = torch.nn.functional.pad(x, (0, 0, 1, 1, 1, 1))  # ZeroPadding2D(1): zeros take part in the max
-        x = tf.max_pool2d(x, 3, 2)
+        if cfg.aa_layer:  # MaxPool2D(3, strides=1) + BlurPool2D(stride=2), resnet.py:532-536
+            x = tf.blur_pool2d(tf.max_pool2d(x, 3, 1), 2)
+        else:
+            x = tf.max_pool2d(x, 3, 2)
     features["stem"] = x
     for j, b in enumerate(_plan(cfg)):
         x = block(x, w, b, cfg)

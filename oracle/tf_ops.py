@@ -59,7 +59,34 @@ def norm(x, weights, prefix, kind):
         eps = 1e-5 if kind == "batch_norm" else 1e-3
         return batch_norm(x, weights[f"{prefix}/gamma"], weights[f"{prefix}/beta"],
                           weights[f"{prefix}/moving_mean"], weights[f"{prefix}/moving_variance"], eps)
+    if kind in ("group_norm", "group_norm_1grp"):
+        return group_norm(x, weights[f"{prefix}/gamma"], weights[f"{prefix}/beta"],
+                          32 if kind == "group_norm" else 1, 1e-5)
     raise ValueError(f"Unknown normalization layer: {kind}")
+
+
+def group_norm(x, gamma, beta, nb_groups, eps):
+    """group_normalize (tfimm/layers/norm.py:22-101): NHWC -> N,H,W,G,S; moments over every axis except N and G
+    (biased variance); per-channel gamma / beta."""
+    shape = x.shape
+    c = shape[-1]
+    xg = x.reshape(shape[0], -1, nb_groups, c // nb_groups)
+    mean = xg.mean(dim=(1, 3), keepdim=True)
+    var = ((xg - mean) ** 2).mean(dim=(1, 3), keepdim=True)
+    xg = (xg - mean) * torch.rsqrt(var + eps)
+    return xg.reshape(shape) * gamma + beta
+
+
+def blur_pool2d(x, stride=2):
+    """BlurPool2D.call (tfimm/layers/blurpool.py:54-62), kernel_size 3: REFLECT pad by (3 + stride) // 2 - 1,
+    then a VALID depthwise convolution with [[1,2,1],[2,4,2],[1,2,1]] / 16 and the given stride."""
+    p = (3 + stride) // 2 - 1
+    xc = x.permute(0, 3, 1, 2)
+    xc = torch.nn.functional.pad(xc, (p, p, p, p), mode="reflect")
+    k1 = torch.tensor([1.0, 2.0, 1.0], dtype=x.dtype)
+    k = (k1[:, None] * k1[None, :] / 16.0)[None, None].repeat(x.shape[-1], 1, 1, 1)
+    y = torch.nn.functional.conv2d(xc, k, stride=stride, groups=x.shape[-1])
+    return y.permute(0, 2, 3, 1)
 
 
 def same_padding(size, k, s, d=1):

@@ -67,7 +67,10 @@ int dwconv_ln(const void*, int, const float*, const float*, const float*, const 
 int dwconv_bias_act(const void*, int, const float*, const float*, void*, float*, int, int, int, int, int, int,
                     int, int, int, int, int, cudaStream_t);
 int global_avg_pool(const void*, int, float*, int, int, int, cudaStream_t);
-int im2col(const void*, int, void*, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int im2col(const void*, int, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int group_norm(const void*, int, const float*, const float*, const void*, void*, float*, int, int, int, int, float, int,
+               cudaStream_t);
+int blur_pool(const void*, int, void*, int, int, int, int, int, int, int, cudaStream_t);
 int se_gate(const float*, float, const float*, const float*, const float*, const float*, float*, int, int, int,
             int, int, cudaStream_t);
 int scale_channels(void*, int, const float*, int, int, int, cudaStream_t);
@@ -187,9 +190,21 @@ int tfimm_b200_global_avg_pool(const void* x, int dtype, float* out, int B, int 
   return tfimm::global_avg_pool(x, dtype, out, B, HW, C, S(stream));
 }
 
-int tfimm_b200_im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int ks,
-                      int stride, int pad_t, int pad_l, int Ho, int Wo, int Kpad, void* stream) {
-  return tfimm::im2col(x, in_dtype, out, out_dtype, B, H, W, C, ks, stride, pad_t, pad_l, Ho, Wo, Kpad, S(stream));
+int tfimm_b200_im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int groups,
+                      int ks, int stride, int pad_t, int pad_l, int Ho, int Wo, int Kpad, void* stream) {
+  return tfimm::im2col(x, in_dtype, out, out_dtype, B, H, W, C, groups, ks, stride, pad_t, pad_l, Ho, Wo, Kpad,
+                       S(stream));
+}
+
+int tfimm_b200_group_norm(const void* x, int dtype, const float* gamma, const float* beta, const void* residual,
+                          void* out, float* stats, int B, int HW, int C, int groups, float eps, int act,
+                          void* stream) {
+  return tfimm::group_norm(x, dtype, gamma, beta, residual, out, stats, B, HW, C, groups, eps, act, S(stream));
+}
+
+int tfimm_b200_blur_pool(const void* x, int dtype, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo,
+                         void* stream) {
+  return tfimm::blur_pool(x, dtype, out, B, H, W, C, stride, Ho, Wo, S(stream));
 }
 
 int tfimm_b200_se_gate(const float* pooled_sum, float inv_hw, const float* w_reduce, const float* b_reduce,

@@ -259,19 +259,24 @@ __global__ void global_avg_pool_kernel(const T* __restrict__ x, float* __restric
 // ----------------------------------------------------------------------------------------------
 // im2col for dense k x k convolutions that are then run as tcgen05 GEMMs
 // ----------------------------------------------------------------------------------------------
-// out[(b, oy, ox), (ky, kx, c)] = x[b, oy*s + ky - pad_t, ox*s + kx - pad_l, c] (0 outside), columns padded
-// with zeros to Kpad.  Column order == TF conv kernel (kh, kw, cin, :) flattened.
+// out[g][(b, oy, ox)][(ky, kx, c)] = x[b, oy*s + ky - pad_t, ox*s + kx - pad_l, g*cg + c] (0 outside), c < cg = C / G,
+// columns padded with zeros to Kpad.  G = 1 is the plain im2col; column order == TF conv kernel (kh, kw, cin, :)
+// flattened.  G > 1 lays the groups of a grouped convolution out as G separate [M][Kpad] matrices, one GEMM each.
 template <typename InT, typename OutT>
-__global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out, int B, int H, int W, int C,
+__global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out, int B, int H, int W, int C, int G,
                               int Ho, int Wo, int ks, int stride, int pad_t, int pad_l, int Kpad) {
-  const int K = ks * ks * C;
+  const int cg = C / G;
+  const int K = ks * ks * cg;
   const int chunks = Kpad >> 3;
-  const long total = (long)B * Ho * Wo * chunks;
-  const bool vec = (C & 7) == 0;  // 8 consecutive columns stay inside one (ky, kx) pixel
+  const long M = (long)B * Ho * Wo;
+  const long total = M * chunks * G;
+  const bool vec = (cg & 7) == 0;  // 8 consecutive columns stay inside one (ky, kx) pixel
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long)gridDim.x * blockDim.x) {
     const int ch = (int)(idx % chunks);
-    const long m = idx / chunks;
+    const long gm = idx / chunks;
+    const long m = gm % M;
+    const int coff = (int)(gm / M) * cg;
     const int ox = (int)(m % Wo);
     const long t = m / Wo;
     const int oy = (int)(t % Ho);
@@ -279,11 +284,11 @@ __global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out,
     const int k0 = ch * 8;
     float v[8];
     if (vec) {
-      const int tap = k0 / C, c = k0 % C;
+      const int tap = k0 / cg, c = k0 % cg;
       const int ky = tap / ks, kx = tap % ks;
       const int iy = oy * stride + ky - pad_t, ix = ox * stride + kx - pad_l;
       if (k0 < K && iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        ld8(x + ((b * H + iy) * W + ix) * (long)C + c, v);
+        ld8(x + ((b * H + iy) * W + ix) * (long)C + coff + c, v);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -294,15 +299,16 @@ __global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out,
         const int k = k0 + j;
         float val = 0.f;
         if (k < K) {
-          const int tap = k / C, c = k % C;
+          const int tap = k / cg, c = k % cg;
           const int ky = tap / ks, kx = tap % ks;
           const int iy = oy * stride + ky - pad_t, ix = ox * stride + kx - pad_l;
-          if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = ld_as_float(x + ((b * H + iy) * W + ix) * (long)C + c);
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+            val = ld_as_float(x + ((b * H + iy) * W + ix) * (long)C + coff + c);
         }
         v[j] = val;
       }
     }
-    st8(out + m * Kpad + k0, v);
+    st8(out + gm * Kpad + k0, v);
   }
 }
 
@@ -410,15 +416,17 @@ inline unsigned conv_grid_for(long total, int threads) {
 
 }  // namespace
 
-int im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int ks, int stride,
-           int pad_t, int pad_l, int Ho, int Wo, int Kpad, cudaStream_t stream) {
+int im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int groups, int ks,
+           int stride, int pad_t, int pad_l, int Ho, int Wo, int Kpad, cudaStream_t stream) {
   TFIMM_CHECK_ARG(B > 0 && ks > 0 && stride > 0 && Ho > 0 && Wo > 0, "im2col: bad geometry");
-  TFIMM_CHECK_ARG(Kpad % 8 == 0 && Kpad >= ks * ks * C, "im2col: Kpad must be a multiple of 8 and >= k*k*C");
-  const long total = (long)B * Ho * Wo * (Kpad / 8);
+  TFIMM_CHECK_ARG(groups > 0 && C % groups == 0, "im2col: C must be divisible by groups (C=%d groups=%d)", C, groups);
+  TFIMM_CHECK_ARG(Kpad % 8 == 0 && Kpad >= ks * ks * (C / groups),
+                  "im2col: Kpad must be a multiple of 8 and >= k*k*C/groups");
+  const long total = (long)B * Ho * Wo * (Kpad / 8) * groups;
   const unsigned grid = conv_grid_for(total, 256);
 #define TFIMM_I2C(IN, OUT)                                                                              \
   im2col_kernel<IN, OUT><<<grid, 256, 0, stream>>>(reinterpret_cast<const IN*>(x), reinterpret_cast<OUT*>(out), \
-                                                  B, H, W, C, Ho, Wo, ks, stride, pad_t, pad_l, Kpad)
+                                                  B, H, W, C, groups, Ho, Wo, ks, stride, pad_t, pad_l, Kpad)
   if (in_dtype == kF32 && out_dtype == kBF16) TFIMM_I2C(float, __nv_bfloat16);
   else if (in_dtype == kBF16 && out_dtype == kBF16) TFIMM_I2C(__nv_bfloat16, __nv_bfloat16);
   else if (in_dtype == kF32 && out_dtype == kF32) TFIMM_I2C(float, float);

@@ -96,6 +96,104 @@ inline unsigned rgrid(long total, int threads) {
   return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+// ---- GroupNormalization (tfimm/layers/norm.py:22-101), NHWC, groups of C/G consecutive channels --------------
+// Pass 1: one CTA per (image, group): mean and rstd over HW x (C/G) values (two sweeps: mean, then centred
+// second moment -- the second sweep hits L2).  Pass 2: elementwise normalise + per-channel affine (+ residual,
+// activation).  Only resnet50_gn uses it, so the kernels favour simplicity over the last GB/s.
+template <typename T>
+__global__ void __launch_bounds__(256)
+group_norm_stats_kernel(const T* __restrict__ x, float* __restrict__ stats /*[B][G][2]*/, int HW, int C, int G,
+                        float eps) {
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  const int cg = C / G;
+  const T* base = x + (long)b * HW * C + g * cg;
+  const long n = (long)HW * cg;
+  __shared__ float red[8];
+  __shared__ float s_mean;
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+  };
+  float s = 0.f;
+  for (long i = threadIdx.x; i < n; i += 256) s += ld_as_float(base + (i / cg) * C + (i % cg));
+  const float mean = block_sum(s) / (float)n;
+  float q = 0.f;
+  for (long i = threadIdx.x; i < n; i += 256) {
+    const float d = ld_as_float(base + (i / cg) * C + (i % cg)) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float var = block_sum(q) / (float)n;
+  if (threadIdx.x == 0) {
+    stats[(long)blockIdx.x * 2] = mean;
+    stats[(long)blockIdx.x * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+template <typename T>
+__global__ void group_norm_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        const T* __restrict__ residual, T* __restrict__ out, long total, int HW, int C,
+                                        int G, int act) {
+  const int cg = C / G;
+  const int chunks = C >> 3;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(idx % chunks) * 8;
+    const long pix = idx / chunks;
+    const long b = pix / HW;
+    float v[8], r[8];
+    ld8(x + pix * C + c0, v);
+    if (residual != nullptr) ld8(residual + pix * C + c0, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float* st = stats + (b * G + c / cg) * 2;
+      float y = (v[j] - st[0]) * st[1] * __ldg(gamma + c) + __ldg(beta + c);
+      if (residual != nullptr) y += r[j];
+      v[j] = apply_act<true>(y, act);
+    }
+    st8(out + pix * C + c0, v);
+  }
+}
+
+// ---- BlurPool2D (tfimm/layers/blurpool.py:54-62): REFLECT pad 1, 3x3 [1 2 1]x[1 2 1]/16, stride s ------------
+template <typename T>
+__global__ void blur_pool_kernel(const T* __restrict__ x, T* __restrict__ out, long total, int H, int W, int C, int Ho,
+                                 int Wo, int stride) {
+  const int chunks = C >> 3;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(idx % chunks) * 8;
+    long t = idx / chunks;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const long b = t / Ho;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      int iy = oy * stride + ky - 1;
+      iy = iy < 0 ? -iy : (iy >= H ? 2 * H - 2 - iy : iy);  // REFLECT (no edge repeat)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        int ix = ox * stride + kx - 1;
+        ix = ix < 0 ? -ix : (ix >= W ? 2 * W - 2 - ix : ix);
+        const float wgt = (float)((ky == 1 ? 2 : 1) * (kx == 1 ? 2 : 1)) * (1.0f / 16.0f);
+        float v[8];
+        ld8(x + ((b * H + iy) * W + ix) * (long)C + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
+      }
+    }
+    st8(out + ((b * Ho + oy) * Wo + ox) * (long)C + c0, acc);
+  }
+}
+
 }  // namespace
 
 int grouped_conv(const void* x, int dtype, const float* wgt, const float* bias, void* out, int B, int H, int W,
@@ -149,6 +247,45 @@ int scale_add_act(void* x, int dtype, const float* gate, const void* shortcut, i
     return kInvalidArgument;
   }
   TFIMM_LAUNCH_OK("scale_add_act_kernel");
+  return kOk;
+}
+
+int group_norm(const void* x, int dtype, const float* gamma, const float* beta, const void* residual, void* out,
+               float* stats, int B, int HW, int C, int groups, float eps, int act, cudaStream_t stream) {
+  TFIMM_CHECK_ARG(B > 0 && HW > 0 && groups > 0 && C % groups == 0 && C % 8 == 0,
+                  "group_norm: need C%%groups==0 and C%%8==0 (C=%d groups=%d)", C, groups);
+  const long total = (long)B * HW * (C / 8);
+#define TFIMM_GN(T)                                                                                               \
+  group_norm_stats_kernel<T><<<B * groups, 256, 0, stream>>>(reinterpret_cast<const T*>(x), stats, HW, C, groups, eps); \
+  group_norm_apply_kernel<T><<<rgrid(total, 256), 256, 0, stream>>>(                                              \
+      reinterpret_cast<const T*>(x), stats, gamma, beta, reinterpret_cast<const T*>(residual),                      \
+      reinterpret_cast<T*>(out), total, HW, C, groups, act)
+  if (dtype == kBF16) { TFIMM_GN(__nv_bfloat16); }
+  else if (dtype == kF32) { TFIMM_GN(float); }
+  else {
+    set_last_error("group_norm: dtype must be bf16 or f32");
+    return kInvalidArgument;
+  }
+#undef TFIMM_GN
+  TFIMM_LAUNCH_OK("group_norm kernels");
+  return kOk;
+}
+
+int blur_pool(const void* x, int dtype, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo,
+              cudaStream_t stream) {
+  TFIMM_CHECK_ARG(B > 0 && H > 1 && W > 1 && C % 8 == 0 && stride > 0, "blur_pool: need H,W>1 and C%%8==0 (C=%d)", C);
+  const long total = (long)B * Ho * Wo * (C / 8);
+  if (dtype == kBF16)
+    blur_pool_kernel<<<rgrid(total, 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                           reinterpret_cast<__nv_bfloat16*>(out), total, H, W, C, Ho, Wo, stride);
+  else if (dtype == kF32)
+    blur_pool_kernel<<<rgrid(total, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(x),
+                                                           reinterpret_cast<float*>(out), total, H, W, C, Ho, Wo, stride);
+  else {
+    set_last_error("blur_pool: dtype must be bf16 or f32");
+    return kInvalidArgument;
+  }
+  TFIMM_LAUNCH_OK("blur_pool_kernel");
   return kOk;
 }
 

@@ -28,6 +28,7 @@ from ._zoo import register_zoo
 __all__ = ["ResNet", "ResNetConfig"]
 
 _BN_EPS = {"batch_norm": 1e-5, "batch_norm_tf": 1e-3}
+_GN_GROUPS = {"group_norm": 32, "group_norm_1grp": 1}  # norm_layer_factory, tfimm/layers/factory.py:49-56; eps 1e-5
 
 
 @dataclass
@@ -133,10 +134,10 @@ class ResNet(Model):
     def __init__(self, cfg: ResNetConfig, *args, **kwargs):
         if isinstance(cfg, dict):
             cfg = ResNetConfig(**cfg)
-        if cfg.norm_layer not in _BN_EPS:
+        if cfg.norm_layer not in _BN_EPS and cfg.norm_layer not in _GN_GROUPS:
             raise NotImplementedError(f"norm_layer={cfg.norm_layer} is not implemented in the B200 engine.")
-        if cfg.aa_layer:
-            raise NotImplementedError("Anti-aliased (BlurPool) ResNets are not implemented in the B200 engine.")
+        if cfg.aa_layer not in ("", "blur_pool"):
+            raise ValueError(f"Unknown anti-aliasing layer {cfg.aa_layer}")
         if cfg.attn_layer not in ("", "se", "eca"):
             raise ValueError(f"Unknown attention layer {cfg.attn_layer}")
         if cfg.global_pool != "avg":
@@ -145,11 +146,8 @@ class ResNet(Model):
             raise ValueError(f"Unknown downsample mode {cfg.downsample_mode}")
         ops.act_code(cfg.act_layer)
         self.blocks = resolve_blocks(cfg)
-        for b in self.blocks:
-            if b.groups > 1 and b.width // b.groups not in (4, 8, 16, 32):
-                raise NotImplementedError(
-                    f"Grouped conv with {b.width // b.groups} channels per group is not implemented "
-                    "(supported: 4, 8, 16, 32).")
+        if cfg.norm_layer in _GN_GROUPS and cfg.cardinality > 1:
+            raise NotImplementedError("GroupNorm with grouped convolutions is not implemented (no registration uses it).")
         super().__init__(cfg, *args, **kwargs)
 
     # ------------------------------------------------------------------ parameters
@@ -175,6 +173,8 @@ class ResNet(Model):
             zero = last and c.zero_init_last_bn
             s[f"{prefix}/gamma"] = ParamSpec((ch,), "zeros" if zero else "ones")
             s[f"{prefix}/beta"] = ParamSpec((ch,), "zeros")
+            if c.norm_layer in _GN_GROUPS:
+                return
             s[f"{prefix}/moving_mean"] = ParamSpec((ch,), "zeros", trainable=False)
             s[f"{prefix}/moving_variance"] = ParamSpec((ch,), "zeros" if zero else "ones", trainable=False)
 
@@ -224,15 +224,32 @@ class ResNet(Model):
         return scale, b - m * scale
 
     def _folded_conv(self, conv_prefix, bn_prefix):
-        scale, shift = self._bn_scale_shift(bn_prefix)
-        w = self.params[f"{conv_prefix}/kernel"].float() * scale
+        """-> (W [out][K] in the activation dtype, bias or None, (gamma, beta) of a GroupNorm or None).
+        BatchNorm (inference) is folded into W and the bias; GroupNorm needs the data and runs as its own kernel."""
+        w = self.params[f"{conv_prefix}/kernel"].float()
+        if self.cfg.norm_layer in _GN_GROUPS:
+            shift, gn = None, (self._vec(f"{bn_prefix}/gamma"), self._vec(f"{bn_prefix}/beta"))
+        else:
+            scale, shift = self._bn_scale_shift(bn_prefix)
+            w, shift, gn = w * scale, shift.contiguous(), None
         cout = w.shape[-1]
         w2 = w.reshape(-1, cout).t().contiguous()
         K = w2.shape[1]
         Kpad = (K + 7) // 8 * 8
         if Kpad != K:
             w2 = torch.nn.functional.pad(w2, (0, Kpad - K))
-        return w2.to(self.act_dtype).contiguous(), shift.contiguous()
+        return w2.to(self.act_dtype).contiguous(), shift, gn
+
+    def _folded_grouped_wide(self, conv_prefix, bn_prefix, groups):
+        """Grouped 3x3 with >= 48 channels per group: one [cg][Kpad] GEMM weight per group (see _grouped_wide)."""
+        scale, shift = self._bn_scale_shift(bn_prefix)
+        w = self.params[f"{conv_prefix}/kernel"].float() * scale        # (k, k, cg, C)
+        k, _, cg, C = w.shape
+        wg = w.reshape(k * k * cg, groups, C // groups).permute(1, 2, 0)  # (G, cg_out, k*k*cg)
+        Kpad = (k * k * cg + 7) // 8 * 8
+        if Kpad != k * k * cg:
+            wg = torch.nn.functional.pad(wg, (0, Kpad - k * k * cg))
+        return wg.to(self.act_dtype).contiguous(), shift.contiguous()
 
     def _folded_grouped(self, conv_prefix, bn_prefix):
         scale, shift = self._bn_scale_shift(bn_prefix)
@@ -249,8 +266,10 @@ class ResNet(Model):
         for b in self.blocks:
             p, d = b.name, {}
             d["conv1"] = self._folded_conv(f"{p}/conv1", f"{p}/bn1")
-            if b.groups > 1:
+            if b.groups > 1 and b.width // b.groups in (4, 8, 16, 32):
                 d["conv2g"] = self._folded_grouped(f"{p}/conv2", f"{p}/bn2")
+            elif b.groups > 1:
+                d["conv2w"] = self._folded_grouped_wide(f"{p}/conv2", f"{p}/bn2", b.groups)
             else:
                 d["conv2"] = self._folded_conv(f"{p}/conv2", f"{p}/bn2")
             if c.block == "bottleneck":
@@ -272,15 +291,34 @@ class ResNet(Model):
 
     # ------------------------------------------------------------------ forward
     def _conv(self, x, wb, k, stride, pad, act, residual=None, act_after_residual=False):
-        w, bias = wb
+        w, bias, gn = wb
         B = x.shape[0]
         if k == 1 and stride == 1:
             cols, Ho, Wo = x.reshape(-1, x.shape[-1]), x.shape[1], x.shape[2]
         else:
             cols, Ho, Wo = ops.im2col(x, k, stride, pad, self.act_dtype)
+        if gn is not None:
+            # conv -> GroupNorm (-> + shortcut) -> act: the norm needs the whole (H, W, C/G) extent, so it cannot be
+            # an epilogue of the GEMM tile; residual and activation ride on the normalisation pass instead
+            assert residual is None or act_after_residual
+            y = ops.gemm(cols, w).view(B, Ho, Wo, w.shape[0])
+            return ops.group_norm(y, *gn, _GN_GROUPS[self.cfg.norm_layer], 1e-5, act=act,
+                                  residual=residual.contiguous() if residual is not None else None)
         res2d = residual.reshape(-1, residual.shape[-1]) if residual is not None else None
         y = ops.gemm(cols, w, bias=bias, act=act, residual=res2d, act_after_residual=act_after_residual)
         return y.view(B, Ho, Wo, w.shape[0])
+
+    def _grouped_wide(self, x, wb, b: _Block, stride, act):
+        """Grouped 3x3 convolution with wide groups (ResNeXt 32x8d .. 32x48d: 48-384 channels per group): grouped
+        im2col (one [M][9*cg] matrix per group) and one tensor-core GEMM per group, written straight into the
+        group's column slice of the output.  Narrow groups (<= 32 channels) use the direct kernel instead."""
+        wg, shift = wb
+        G, cg = wg.shape[0], wg.shape[1]
+        cols, Ho, Wo = ops.im2col(x, 3, stride, 1, self.act_dtype, groups=G)
+        out = torch.empty((cols.shape[1], G * cg), device=x.device, dtype=self.act_dtype)
+        for g in range(G):
+            ops.gemm(cols[g], wg[g], bias=shift[g * cg:(g + 1) * cg], act=act, out=out[:, g * cg:(g + 1) * cg])
+        return out.view(x.shape[0], Ho, Wo, G * cg)
 
     def _shortcut(self, x, b: _Block, d):
         c = self.cfg
@@ -298,16 +336,25 @@ class ResNet(Model):
         act = c.act_layer
         shortcut = self._shortcut(x, b, d)
         plain = b.attn == ""
+        # anti-aliased variants: the strided conv runs at stride 1 and BlurPool2D takes the stride (resnet.py:127-140)
+        use_aa = bool(c.aa_layer) and b.stride == 2
+        cstride = 1 if use_aa else b.stride
         if c.block == "basic_block":
-            h = self._conv(x, d["conv1"], 3, b.stride, 1, act)
+            h = self._conv(x, d["conv1"], 3, cstride, 1, act)
+            if use_aa:
+                h = ops.blur_pool(h, b.stride)
             h = self._conv(h, d["conv2"], 3, 1, 1, act if plain else None,
                            residual=shortcut if plain else None, act_after_residual=plain)
         else:
             h = self._conv(x, d["conv1"], 1, 1, 0, act)
-            if b.groups > 1:
-                h = ops.grouped_conv(h, *d["conv2g"], b.width // b.groups, 3, b.stride, 1, act=act)
+            if "conv2g" in d:
+                h = ops.grouped_conv(h, *d["conv2g"], b.width // b.groups, 3, cstride, 1, act=act)
+            elif "conv2w" in d:
+                h = self._grouped_wide(h, d["conv2w"], b, cstride, act)
             else:
-                h = self._conv(h, d["conv2"], 3, b.stride, 1, act)
+                h = self._conv(h, d["conv2"], 3, cstride, 1, act)
+            if use_aa:
+                h = ops.blur_pool(h, b.stride)
             h = self._conv(h, d["conv3"], 1, 1, 0, act if plain else None,
                            residual=shortcut if plain else None, act_after_residual=plain)
         if not plain:
@@ -334,6 +381,8 @@ class ResNet(Model):
                 x = self._conv(x, wb, 7, 2, 3, c.act_layer)
         if c.replace_stem_pool:
             x = self._conv(x, P["pool_conv"], 3, 2, 1, c.act_layer)
+        elif c.aa_layer:  # ZeroPadding2D(1) + MaxPool2D(3, strides=1) + BlurPool2D(stride=2), resnet.py:532-536
+            x = ops.blur_pool(ops.pool2d(x, 3, 1, 1, "max_zero_pad"), 2)
         else:
             x = ops.pool2d(x, 3, 2, 1, "max_zero_pad")
         features["stem"] = x

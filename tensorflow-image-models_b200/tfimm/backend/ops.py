@@ -319,17 +319,45 @@ def conv_geometry(H, W, ks, stride, padding):
     return (H + 2 * pd - ks) // stride + 1, (W + 2 * pd - ks) // stride + 1, pd, pd
 
 
-def im2col(x, ks, stride, padding, out_dtype):
-    """x: (B,H,W,C) -> ((B*Ho*Wo, ceil8(ks*ks*C)), Ho, Wo)."""
+def im2col(x, ks, stride, padding, out_dtype, groups=1):
+    """x: (B,H,W,C) -> ((B*Ho*Wo, ceil8(ks*ks*C)), Ho, Wo); groups > 1: ((groups, B*Ho*Wo, ceil8(ks*ks*C/groups)), ...)
+    with one im2col matrix per channel group."""
+    _cuda(x)
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and C % groups == 0
+    Ho, Wo, pt, pl = conv_geometry(H, W, ks, stride, padding)
+    Kpad = (ks * ks * (C // groups) + 7) // 8 * 8
+    shape = (B * Ho * Wo, Kpad) if groups == 1 else (groups, B * Ho * Wo, Kpad)
+    out = torch.empty(shape, device=x.device, dtype=out_dtype)
+    _call("tfimm_b200_im2col", x.data_ptr(), _code(x), out.data_ptr(), _code(out), B, H, W, C, groups, ks, stride,
+          pt, pl, Ho, Wo, Kpad, _stream(), nbytes=_nbytes(x, out))
+    return out, Ho, Wo
+
+
+def group_norm(x, gamma, beta, groups, eps, act=None, residual=None):
+    """GroupNormalization over an NHWC tensor, then optional ``+ residual`` and activation."""
+    _cuda(x, gamma, beta, residual)
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and (residual is None or (residual.shape == x.shape and residual.is_contiguous()
+                                                       and residual.dtype == x.dtype))
+    out = torch.empty_like(x)
+    stats = torch.empty((B, groups, 2), device=x.device, dtype=torch.float32)
+    _call("tfimm_b200_group_norm", x.data_ptr(), _code(x), gamma.data_ptr(), beta.data_ptr(), _ptr(residual),
+          out.data_ptr(), stats.data_ptr(), B, H * W, C, groups, float(eps), act_code(act), _stream(),
+          nbytes=_nbytes(x, x, out, residual))
+    return out
+
+
+def blur_pool(x, stride=2):
+    """BlurPool2D: REFLECT pad 1, 3x3 binomial blur, stride."""
     _cuda(x)
     B, H, W, C = x.shape
     assert x.is_contiguous()
-    Ho, Wo, pt, pl = conv_geometry(H, W, ks, stride, padding)
-    Kpad = (ks * ks * C + 7) // 8 * 8
-    out = torch.empty((B * Ho * Wo, Kpad), device=x.device, dtype=out_dtype)
-    _call("tfimm_b200_im2col", x.data_ptr(), _code(x), out.data_ptr(), _code(out), B, H, W, C, ks, stride, pt, pl,
-          Ho, Wo, Kpad, _stream(), nbytes=_nbytes(x, out))
-    return out, Ho, Wo
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty((B, Ho, Wo, C), device=x.device, dtype=x.dtype)
+    _call("tfimm_b200_blur_pool", x.data_ptr(), _code(x), out.data_ptr(), B, H, W, C, stride, Ho, Wo, _stream(),
+          nbytes=_nbytes(x, out))
+    return out
 
 
 def se_gate(pooled_sum, hw, w_reduce, b_reduce, w_expand, b_expand, act, gate_act="sigmoid"):

@@ -541,3 +541,57 @@ def test_gemm_act_after_residual():
     torch.cuda.synchronize()
     ref = torch.relu(a.float() @ w.float().t() + bias + res.float())
     assert (out.float() - ref).abs().max().item() < 2e-2 + 4e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,groups", [(64, 32), (256, 32), (2048, 32), (64, 1)])
+def test_group_norm_with_residual_and_act(C, groups, dtype):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(C + groups)
+    x = (torch.randn(3, 7, 9, C, device="cuda", generator=g) * 2 + 0.5).to(dtype)
+    res = torch.randn(3, 7, 9, C, device="cuda", generator=g).to(dtype)
+    gamma, beta = torch.randn(C, device="cuda", generator=g), torch.randn(C, device="cuda", generator=g)
+    out = ops.group_norm(x, gamma, beta, groups, 1e-5, act="relu", residual=res)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), groups, gamma, beta, 1e-5).permute(0, 2, 3, 1)
+    ref = torch.relu(ref + res.float())
+    tol = 2e-5 if dtype == torch.float32 else 2.0 ** -8 * ref.abs().max().item() + 1e-3
+    assert (out.float() - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H,W,stride", [(8, 8, 2), (7, 9, 2), (5, 4, 1)])
+def test_blur_pool_reflect(H, W, stride, dtype):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(H * W)
+    x = torch.randn(2, H, W, 24, device="cuda", generator=g).to(dtype)
+    out = ops.blur_pool(x, stride)
+    torch.cuda.synchronize()
+    xc = torch.nn.functional.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect")
+    k1 = torch.tensor([1.0, 2.0, 1.0], device="cuda")
+    k = (k1[:, None] * k1[None, :] / 16)[None, None].repeat(24, 1, 1, 1)
+    ref = torch.nn.functional.conv2d(xc, k, stride=stride, groups=24).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert (out.float() - ref).abs().max().item() < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("cg,stride", [(64, 1), (48, 2), (24, 1)])
+def test_grouped_im2col_and_per_group_gemm_equal_grouped_conv(cg, stride):
+    ops = _ops()
+    G, B, H, W = 4, 2, 9, 11
+    C = G * cg
+    g = torch.Generator(device="cuda").manual_seed(cg)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(3, 3, cg, C, device="cuda", generator=g) / (3 * cg ** 0.5)          # TF layout (kh, kw, cin/G, cout)
+    cols, Ho, Wo = ops.im2col(x, 3, stride, 1, torch.bfloat16, groups=G)
+    assert cols.shape[0] == G and cols.shape[1] == B * Ho * Wo
+    wg = w.reshape(9 * cg, G, cg).permute(1, 2, 0)
+    wg = torch.nn.functional.pad(wg, (0, cols.shape[2] - 9 * cg)).to(torch.bfloat16).contiguous()
+    out = torch.empty(B * Ho * Wo, C, device="cuda", dtype=torch.bfloat16)
+    for i in range(G):
+        ops.gemm(cols[i], wg[i], out=out[:, i * cg:(i + 1) * cg])
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float().permute(3, 2, 0, 1),
+                                     stride=stride, padding=1, groups=G).permute(0, 2, 3, 1).reshape(-1, C)
+    assert (out.float() - ref).abs().max().item() < 2e-2 + 4e-3 * ref.abs().max().item()
+

@@ -61,6 +61,18 @@ def test_vit_bf16_parity(name, batch):
     assert rel < BF16_TOL
 
 
+@pytest.mark.parametrize("name", ["vit_tiny_patch16_224", "vit_base_patch16_224"])
+def test_vit_bf16_parity_with_folded_layernorm(name, monkeypatch):
+    """Opt-in path: norm1/norm2 folded into the qkv / fc1 GEMMs (raw bf16 rows + per-row statistics)."""
+    monkeypatch.setenv("TFIMM_B200_LN_FOLD", "1")
+    from tfimm.backend import ops
+    before = ops.launch_count
+    _, _, _, out, ref = _run(name, "vit", "bf16", 2)
+    rel, ab = _nerr(out, ref)
+    print(f"{name} bf16 (LN folded): normalised {rel:.3e} abs {ab:.3e}, {ops.launch_count - before} launches")
+    assert rel < BF16_TOL
+
+
 def test_vit_return_features_matches_plain_call():
     """reference tests/models/test_factory.py:205-222: same logits, exactly `feature_names` keys."""
     import tfimm
@@ -223,6 +235,20 @@ def test_resnet_fp32_parity(name):
     print(f"{name} fp32: normalised {rel:.3e} abs {ab:.3e}")
     assert out.shape == ref.shape
     assert rel < FP32_TOL
+
+
+@pytest.mark.parametrize("name,overrides", [
+    ("resnet50_gn", {}),                                       # GroupNormalization instead of every BatchNorm
+    ("resnetblur50", {}),                                      # BlurPool2D anti-aliasing (stem pool + strided blocks)
+    ("resnext101_32x8d", {"nb_blocks": (1, 1, 1, 1)}),         # 64 channels per group in the last stage
+    ("ig_resnext101_32x48d", {"nb_blocks": (1, 1, 1, 1), "input_size": (64, 64)}),  # 48..384 channels per group
+])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_resnet_norm_blur_and_wide_group_variants(name, overrides, precision):
+    _, _, _, out, ref = _run(name, "resnet", precision, 2, overrides)
+    rel, ab = _nerr(out, ref)
+    print(f"{name} {precision}: normalised {rel:.3e} abs {ab:.3e}")
+    assert rel < (FP32_TOL if precision == "fp32" else BF16_TOL)
 
 
 @pytest.mark.parametrize("name", ["resnet50", "resnext50_32x4d"])

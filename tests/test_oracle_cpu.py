@@ -100,6 +100,23 @@ def test_roll_and_dense_and_softmax():
     assert torch.allclose(s, torch.tensor([[0.5, 0.5]]))
 
 
+def test_group_norm_matches_torch_and_blur_pool_matches_direct_sum():
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 5, 6, 64, generator=g, dtype=torch.float64)
+    gamma, beta = torch.randn(64, generator=g, dtype=torch.float64), torch.randn(64, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5).permute(0, 2, 3, 1)
+    assert (tf.group_norm(x, gamma, beta, 32, 1e-5) - ref).abs().max() < 1e-12
+    # BlurPool2D: REFLECT pad 1 (index -1 -> 1, H -> H-2), [1 2 1] x [1 2 1] / 16, stride 2, VALID
+    y = tf.blur_pool2d(x, 2)
+    assert y.shape == (2, 3, 3, 64)
+    k = [1.0, 2.0, 1.0]
+    refl = lambda i, n: -i if i < 0 else (2 * n - 2 - i if i >= n else i)
+    for (oy, ox) in [(0, 0), (2, 2), (1, 0)]:
+        acc = sum(k[a] * k[b] / 16.0 * x[:, refl(2 * oy + a - 1, 5), refl(2 * ox + b - 1, 6)]
+                  for a in range(3) for b in range(3))
+        assert (y[:, oy, ox] - acc).abs().max() < 1e-12
+
+
 def test_avg_pool_same_excludes_padding():
     x = torch.ones(1, 3, 3, 1)
     assert torch.allclose(tf.avg_pool2d_same(x, 2, 2), torch.ones(1, 2, 2, 1))
