@@ -357,7 +357,8 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tcgen05_fence_after();
         float row_sum = 1.f;
         if (warp_has_rows) {
-          float mx = -INFINITY;
+          // four independent running maxima / sums: one accumulator would be a 208-deep dependent chain per row
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
           {
             uint32_t rg[32], cur[32];
             issue(0, rg);
@@ -368,16 +369,17 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
               if (c + 1 < nchunks) issue(c + 1, rg);
               if (c * 32 + 32 <= N) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
+                for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(cur[j]));
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (c * 32 + j < N) mx = fmaxf(mx, __uint_as_float(cur[j]));
+                  if (c * 32 + j < N) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(cur[j]));
               }
             }
           }
+          const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
           const uint64_t nmoff = splat2(-mx * scale_log2);
-          uint64_t sum2 = splat2(0.f);
+          uint64_t sum4[4] = {splat2(0.f), splat2(0.f), splat2(0.f), splat2(0.f)};
           {
             uint32_t rg[32], cur[32];
             issue(0, rg);
@@ -397,7 +399,7 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                   p0 = (c * 32 + 2 * j < N) ? p0 : 0.f;
                   p1 = (c * 32 + 2 * j + 1 < N) ? p1 : 0.f;
                 }
-                sum2 = add2(sum2, pack2(p0, p1));
+                sum4[j & 3] = add2(sum4[j & 3], pack2(p0, p1));
                 pk[j] = pack_bf16x2(p0, p1);
               }
               uint32_t lo[8], hi[8];
@@ -409,7 +411,7 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           }
           tmem_st_wait();
           float s0, s1;
-          unpack2(sum2, s0, s1);
+          unpack2(add2(add2(sum4[0], sum4[1]), add2(sum4[2], sum4[3])), s0, s1);
           row_sum = s0 + s1;
         }
         tcgen05_fence_before();
