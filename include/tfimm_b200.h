@@ -80,6 +80,17 @@ int tfimm_b200_gemm_bf16_ln(const void* A, int lda, const void* W, int ldw, cons
                             const float* ln_stats, int ln_parts, const float* ln_colsum, float ln_eps,
                             void* emit_bf16, int ld_emit, float* emit_stats, int emit_parts, void* stream);
 int tfimm_b200_gemm_stat_parts(int M, int N, int force_block_n);
+
+/* Dense k x k convolution (+ folded-BN bias, activation, optional residual, act(x + shortcut)) as an IMPLICIT GEMM
+ * on the tcgen05 tensor cores: tf.keras.layers.ZeroPadding2D(pad) + Conv2D(k, strides) (+ BatchNormalization, act)
+ * at tfimm/architectures/resnet.py:129-150 (BasicBlock 3x3), 230-238 (Bottleneck conv2), 486-512 (deep stems).
+ * x: NHWC bf16 [B][H][W][C], C % 64 == 0; W: bf16 [N][k*k*C] in (ky, kx, c) order (the TF kernel (kh,kw,cin,cout)
+ * flattened and transposed), leading dimension ldw; out / residual: NHWC [B][Ho][Wo][N], bf16 or fp32.
+ * No im2col matrix is materialised: each A tile (128 output pixels x 64 channels of one tap) is one 4-D TMA box
+ * of the input whose out-of-bounds elements are the zero padding; stride 2 is the box's traversal stride. */
+int tfimm_b200_conv_bf16(const void* x, const void* W, int ldw, const float* bias, const void* residual, void* out,
+                         int B, int H, int Wd, int C, int N, int ks, int stride, int pad, int act,
+                         int act_after_residual, int out_dtype, void* stream);
 /* bf16 copy + one (sum, sum of squares) partial per row of an fp32 [rows][C] matrix: entry point of a
  * LayerNorm-folded stream (after the token assembly / patch embedding, which are not GEMM epilogues). */
 int tfimm_b200_row_stats_cast(const float* x, long in_stride, void* out_bf16, long out_stride, float* stats,

@@ -43,6 +43,8 @@ int gemm_bf16_dispatch(const void*, int, const void*, int, const float*, const f
                        int, int, int, int, int, int, int, int, const float*, int, const float*, float, void*, int,
                        float*, int, cudaStream_t);
 int gemm_bf16_stat_parts(int, int, int);
+int conv_bf16_dispatch(const void*, const void*, int, const float*, const void*, void*, int, int, int, int, int, int,
+                       int, int, int, int, int, cudaStream_t);
 int row_stats_cast(const float*, long, void*, long, float*, long, int, cudaStream_t);
 int gemm_f32(const float*, int, const float*, int, const float*, const float*, const float*, int, float*, int,
              int, int, int, int, int, cudaStream_t);
@@ -107,6 +109,13 @@ int tfimm_b200_gemm_bf16_ln(const void* A, int lda, const void* W, int ldw, cons
   return tfimm::gemm_bf16_dispatch(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act,
                                    act_after_residual, out_dtype, force_block_n, ln_stats, ln_parts, ln_colsum,
                                    ln_eps, emit_bf16, ld_emit, emit_stats, emit_parts, S(stream));
+}
+
+int tfimm_b200_conv_bf16(const void* x, const void* W, int ldw, const float* bias, const void* residual, void* out,
+                         int B, int H, int Wd, int C, int N, int ks, int stride, int pad, int act,
+                         int act_after_residual, int out_dtype, void* stream) {
+  return tfimm::conv_bf16_dispatch(x, W, ldw, bias, residual, out, B, H, Wd, C, N, ks, stride, pad, act,
+                                   act_after_residual, out_dtype, S(stream));
 }
 
 int tfimm_b200_gemm_stat_parts(int M, int N, int force_block_n) {

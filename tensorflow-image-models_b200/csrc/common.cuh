@@ -65,7 +65,8 @@ int sm_count();
 
 // tmap.cu: TMA descriptors (SWIZZLE_128B, zero OOB fill)
 int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, const char* what, int swizzle_bytes = 128);
+              const uint64_t* strides_bytes, const uint32_t* box, const char* what, int swizzle_bytes = 128,
+              const uint32_t* elem_strides = nullptr);
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols, const char* what, int swizzle_bytes = 128);
 
@@ -392,6 +393,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void* tmap,
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2) {

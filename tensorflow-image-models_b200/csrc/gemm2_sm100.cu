@@ -188,7 +188,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const bool last = c + 2 >= nvalid;
         epilogue_chunk<OutT>(p, t_acc + (uint32_t)(c * CH), n0, row0, slab, my_row, lane, res_bar(ew), cc & 1u,
                              &tmap_c, &tmap_r, &tmap_c2, copy_slab, copy_row, ln_rstd, ln_nmr, stat_s, stat_q,
-                             [&]() { if (last) release_acc(); });
+                             /*ct=*/nullptr, [&]() { if (last) release_acc(); });
         ++cc;
       }
       if (p.emit_stats != nullptr) emit_row_stats(p, row0 + lane, 2 * n_blk + grp, 2 * num_n_tiles, stat_s, stat_q);

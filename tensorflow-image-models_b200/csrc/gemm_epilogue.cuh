@@ -30,6 +30,19 @@ struct GemmParams {
   __nv_bfloat16* emit_bf16;  // [M][ld_emit], or null (C itself is bf16 / no copy wanted)
   int ld_emit;
   float* emit_stats;         // [M][2 * ceil(N / tile N)][2], or null
+  // Implicit convolution (gemm_sm100.cu): the A operand is not a matrix but the NHWC input itself.  A tile's 128
+  // rows are a patch of cv_pb images x cv_ph rows x cv_pw columns of OUTPUT pixels; k-block kb is tap
+  // (ky, kx) = kb / (C/64) and 64 input channels, fetched as ONE 4-D TMA box whose out-of-bounds elements are
+  // the zero padding.  C and the residual are NHWC too (4-D stores of pw x 32/pw pixel patches per warp).
+  int conv;                  // 0: plain GEMM
+  int cv_cblocks;            // C / 64
+  int cv_ks, cv_stride, cv_pad;
+  int cv_pb, cv_ph, cv_pw;
+  int cv_tiles_x, cv_tiles_y;  // patch grid per image group (x fastest, then y, then image group)
+};
+
+struct ConvTile {
+  int x, y, b;  // output-pixel coordinates of a warp's first row
 };
 
 // mean / rstd of row `row` from the partial statistics; returned as (rstd, -mean * rstd).
@@ -138,13 +151,16 @@ __device__ __forceinline__ void apply_act_pairs(uint64_t (&v)[NP], int act) {
 //   slab       this warp's 4 KB smem slab (shared::cta address), my_row = generic pointer to this lane's row
 //   res_bar    this warp's residual mbarrier, res_parity = (#chunks this warp has processed) & 1
 //   after_load called once the accumulator values are in registers (caller releases the TMEM stage there)
+//   ct         implicit-convolution mode: where this warp's 32 rows (a pw x 32/pw pixel patch of one image) sit
+//              in the NHWC output; null for a plain row-major C
 template <typename OutT, typename AfterLoad>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_addr, int n0, int row0,
                                                uint32_t slab, uint8_t* my_row, int lane, uint32_t res_bar,
                                                uint32_t res_parity, const CUtensorMap* tmap_c,
                                                const CUtensorMap* tmap_r, const CUtensorMap* tmap_c2,
                                                uint32_t copy_slab, uint8_t* copy_row, float ln_rstd, float ln_nmr,
-                                               float& stat_s, float& stat_q, AfterLoad after_load) {
+                                               float& stat_s, float& stat_q, const ConvTile* ct,
+                                               AfterLoad after_load) {
   constexpr int CH = 128 / (int)sizeof(OutT);
   const int sw = lane & 7;  // TMA SWIZZLE_128B: 16-byte chunk j of row r lives at j ^ (r & 7)
   // the previous store of this warp must have finished reading the slab
@@ -152,7 +168,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_a
     tma_store_wait_read<0>();
     if (p.has_res) {
       mbar_expect_tx(res_bar, kEpiSlabBytes);
-      tma_load_2d(slab, tmap_r, res_bar, n0, row0);
+      if (ct == nullptr) tma_load_2d(slab, tmap_r, res_bar, n0, row0);
+      else tma_load_4d(slab, tmap_r, res_bar, n0, ct->x, ct->y, ct->b);
     }
   }
   __syncwarp();
@@ -250,7 +267,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_a
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
-    tma_store_2d(tmap_c, slab, n0, row0);
+    if (ct == nullptr) tma_store_2d(tmap_c, slab, n0, row0);
+    else tma_store_4d(tmap_c, slab, n0, ct->x, ct->y, ct->b);
     if constexpr (sizeof(OutT) == 4) {
       if (p.emit_bf16 != nullptr) tma_store_2d(tmap_c2, copy_slab, n0, row0);
     }

@@ -120,7 +120,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t sa = smem_tiles + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
+          if (p.conv == 0) {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
+          } else {
+            // implicit convolution: tap (ky, kx) and a 64-channel slice of the input patch; padding = OOB zero fill
+            const int tap = kb / p.cv_cblocks, cb = kb - tap * p.cv_cblocks;
+            const int ky = tap / p.cv_ks, kx = tap - ky * p.cv_ks;
+            const int tx = m_blk % p.cv_tiles_x, tyb = m_blk / p.cv_tiles_x;
+            const int ty = tyb % p.cv_tiles_y, tb = tyb / p.cv_tiles_y;
+            tma_load_4d(sa, &tmap_a, full_bar(stage), cb * kBlockK, tx * p.cv_pw * p.cv_stride + kx - p.cv_pad,
+                        ty * p.cv_ph * p.cv_stride + ky - p.cv_pad, tb * p.cv_pb);
+          }
           tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * BLOCK_N);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -174,6 +184,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / num_n_tiles, n_blk = t % num_n_tiles;
       const int row0 = m_blk * kBlockM + q * 32;
+      ConvTile ctile{0, 0, 0};
+      if (p.conv != 0) {
+        // this warp's 32 rows are a (32 / pw) x pw pixel patch of ONE image of the tile's pb x ph x pw patch
+        const int tx = m_blk % p.cv_tiles_x, tyb = m_blk / p.cv_tiles_x;
+        const int ty = tyb % p.cv_tiles_y, tb = tyb / p.cv_tiles_y;
+        const int per_img = p.cv_ph * p.cv_pw, r0 = q * 32;
+        ctile.b = tb * p.cv_pb + r0 / per_img;
+        ctile.y = ty * p.cv_ph + (r0 % per_img) / p.cv_pw;
+        ctile.x = tx * p.cv_pw;
+      }
+      const ConvTile* ct = p.conv != 0 ? &ctile : nullptr;
       const int cols_left = p.N - n_blk * BLOCK_N;
       const int nvalid = cols_left >= BLOCK_N ? NCH : (cols_left + CH - 1) / CH;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -191,7 +212,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int n0 = n_blk * BLOCK_N + c * CH;
         const bool last = c + 2 >= nvalid;
         epilogue_chunk<OutT>(p, t_acc + (uint32_t)(c * CH), n0, row0, slab, my_row, lane, res_bar(ew), cc & 1u,
-                             &tmap_c, &tmap_r, &tmap_c2, copy_slab, copy_row, ln_rstd, ln_nmr, stat_s, stat_q, [&]() {
+                             &tmap_c, &tmap_r, &tmap_c2, copy_slab, copy_row, ln_rstd, ln_nmr, stat_s, stat_q, ct, [&]() {
                                if (last) {
                                  // all TMEM reads of this accumulator stage by this warp are done
                                  tcgen05_fence_before();
@@ -251,6 +272,48 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, const void* resi
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kernel<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, tc2, p);
   TFIMM_LAUNCH_OK("gemm_bf16_tcgen05_kernel");
+  return kOk;
+}
+
+int pick_block_n(int M, int N);
+
+// Implicit k x k convolution on the tensor cores: same kernel, A tensor map = the NHWC input (rank 4, traversal
+// stride = conv stride), C / residual tensor maps = the NHWC output (rank 4).  See GemmParams::conv.
+template <int BLOCK_N, typename OutT>
+int launch_conv(const void* x, const void* W, int ldw, const void* residual, void* out, int B, int H, int Wd, int C,
+                int Ho, int Wo, GemmParams p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int out_dtype = sizeof(OutT) == 2 ? kBF16 : kF32;
+  constexpr int CH = 128 / (int)sizeof(OutT);
+  const int N = p.N, s = p.cv_stride;
+  CUtensorMap ta, tb, tc, tr;
+  int st;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wd, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)Wd * C * 2, (uint64_t)H * Wd * C * 2};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(p.cv_pw * s), (uint32_t)(p.cv_ph * s), (uint32_t)p.cv_pb};
+    const uint32_t estr[4] = {1u, (uint32_t)s, (uint32_t)s, 1u};
+    if ((st = make_tmap(&ta, x, kBF16, 4, dims, strides, box, "conv input", 128, estr)) != kOk) return st;
+  }
+  if ((st = make_tmap_2d(&tb, W, kBF16, N, p.K, ldw, BLOCK_N, kBlockK, "conv weights")) != kOk) return st;
+  {
+    const uint64_t esz = sizeof(OutT);
+    const uint64_t dims[4] = {(uint64_t)N, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)N * esz, (uint64_t)Wo * N * esz, (uint64_t)Ho * Wo * N * esz};
+    const uint32_t box[4] = {(uint32_t)CH, (uint32_t)p.cv_pw, (uint32_t)(32 / p.cv_pw), 1u};
+    if ((st = make_tmap(&tc, out, out_dtype, 4, dims, strides, box, "conv output")) != kOk) return st;
+    if (residual != nullptr) {
+      if ((st = make_tmap(&tr, residual, out_dtype, 4, dims, strides, box, "conv residual")) != kOk) return st;
+    } else {
+      tr = tc;
+    }
+  }
+  auto kernel = gemm_bf16_tcgen05_kernel<BLOCK_N, OutT>;
+  TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  const int tiles = (p.M / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kernel<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, tc, p);
+  TFIMM_LAUNCH_OK("gemm_bf16_tcgen05_kernel (implicit convolution)");
   return kOk;
 }
 
@@ -342,6 +405,44 @@ int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const flo
       return kInvalidArgument;
   }
 #undef TFIMM_GEMM_CASE
+}
+
+// k x k convolution (stride 1 or 2, symmetric padding (k-1)/2... given as `pad`) + bias + activation (+ residual),
+// NHWC bf16 in, NHWC bf16/fp32 out, W[N][k*k*C] in (ky, kx, c) order: implicit GEMM, no im2col matrix in HBM.
+int conv_bf16_dispatch(const void* x, const void* W, int ldw, const float* bias, const void* residual, void* out,
+                       int B, int H, int Wd, int C, int N, int ks, int stride, int pad, int act, int act_post,
+                       int out_dtype, cudaStream_t stream) {
+  TFIMM_CHECK_ARG(B > 0 && H > 0 && Wd > 0 && C > 0 && C % 64 == 0, "conv: C must be a multiple of 64 (got %d)", C);
+  TFIMM_CHECK_ARG(ks >= 1 && ks <= 7 && (stride == 1 || stride == 2) && pad >= 0 && pad < ks, "conv: bad geometry");
+  TFIMM_CHECK_ARG(N > 0 && N % 8 == 0, "conv: N must be a multiple of 8 (got %d)", N);
+  TFIMM_CHECK_ARG(out_dtype == kBF16 || out_dtype == kF32, "conv: out_dtype must be bf16 or f32");
+  TFIMM_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0, "conv: bias must be 16-byte aligned");
+  const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (Wd + 2 * pad - ks) / stride + 1;
+  TFIMM_CHECK_ARG(Ho > 0 && Wo > 0, "conv: empty output");
+  GemmParams p{};
+  p.N = N; p.K = ks * ks * C;
+  p.bias = bias; p.act = act; p.has_res = residual != nullptr ? 1 : 0; p.act_post = act_post;
+  p.conv = 1; p.cv_cblocks = C / 64; p.cv_ks = ks; p.cv_stride = stride; p.cv_pad = pad;
+  // 128-pixel output patch: 8 x 16 pixels of one image, or 8 x 8 pixels of two images for small feature maps
+  if (Wo > 8) { p.cv_pb = 1; p.cv_ph = 8; p.cv_pw = 16; }
+  else { p.cv_pb = 2; p.cv_ph = 8; p.cv_pw = 8; }
+  p.cv_tiles_x = (Wo + p.cv_pw - 1) / p.cv_pw;
+  p.cv_tiles_y = (Ho + p.cv_ph - 1) / p.cv_ph;
+  const int tiles_b = (B + p.cv_pb - 1) / p.cv_pb;
+  p.M = tiles_b * p.cv_tiles_y * p.cv_tiles_x * kBlockM;  // padded row count: every tile is a full patch
+  const int bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
+#define TFIMM_CONV_CASE(BN)                                                                                       \
+  case BN:                                                                                                        \
+    return out_dtype == kBF16                                                                                     \
+               ? launch_conv<BN, __nv_bfloat16>(x, W, ldw, residual, out, B, H, Wd, C, Ho, Wo, p, stream)           \
+               : launch_conv<BN, float>(x, W, ldw, residual, out, B, H, Wd, C, Ho, Wo, p, stream);
+  switch (bn) {
+    TFIMM_CONV_CASE(256)
+    TFIMM_CONV_CASE(128)
+    TFIMM_CONV_CASE(64)
+  }
+#undef TFIMM_CONV_CASE
+  return kInvalidArgument;
 }
 
 // Number of per-row partial statistics a statistics-emitting GEMM of this shape writes (see gemm_bf16_dispatch).

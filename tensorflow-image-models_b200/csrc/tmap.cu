@@ -26,7 +26,8 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // Generic tiled map, swizzle_bytes in {128, 64, 0 = none}, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..rank-1.
 int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, const char* what, int swizzle_bytes) {
+              const uint64_t* strides_bytes, const uint32_t* box, const char* what, int swizzle_bytes,
+              const uint32_t* elem_strides) {
   auto encode = get_encode_fn();
   if (encode == nullptr) {
     set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -42,7 +43,7 @@ int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides != nullptr ? elem_strides[i] : 1;  // traversal stride (strided convolutions)
     if (i > 0) {
       if ((strides_bytes[i - 1] & 15u) != 0) {
         set_last_error("tensor map %s: stride %llu of dim %d is not a multiple of 16 bytes", what,

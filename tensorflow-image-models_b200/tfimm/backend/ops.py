@@ -53,7 +53,7 @@ def _call(name, *args, flops=0.0, nbytes=0.0):
         e0.record()
         _lib.check(fn(*args), name)
         e1.record()
-        trace.append((name.replace("tfimm_b200_", "").replace("gemm_bf16_ln", "gemm_bf16"), e0, e1, float(flops),
+        trace.append((name.replace("tfimm_b200_", "").replace("gemm_bf16_ln", "gemm_bf16").replace("conv_bf16", "gemm_bf16"), e0, e1, float(flops),
                       float(nbytes)))
     else:
         _lib.check(fn(*args), name)
@@ -143,6 +143,26 @@ def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dty
         _call("tfimm_b200_gemm_f32", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
               _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
               int(bool(act_after_residual)), _stream(), flops=2.0 * M * N * K, nbytes=_nbytes(a, w, out, residual))
+    return out
+
+
+def conv_gemm(x, w, bias=None, ks=3, stride=1, pad=1, act=None, residual=None, act_after_residual=False,
+              out_dtype=None):
+    """Dense k x k convolution as an implicit GEMM (no im2col matrix).  x: (B,H,W,C) bf16 with C % 64 == 0;
+    w: (N, ks*ks*C) bf16 in (ky, kx, c) order; residual / result: (B,Ho,Wo,N)."""
+    _cuda(x, w, bias, residual)
+    B, H, W, C = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_contiguous() and w.stride(1) == 1
+    assert w.shape[1] == ks * ks * C, (w.shape, ks, C)
+    Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    out_dtype = out_dtype or (residual.dtype if residual is not None else x.dtype)
+    out = torch.empty((B, Ho, Wo, N), device=x.device, dtype=out_dtype)
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == out.dtype and residual.is_contiguous()
+    _call("tfimm_b200_conv_bf16", x.data_ptr(), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(residual), out.data_ptr(),
+          B, H, W, C, N, ks, stride, pad, act_code(act), int(bool(act_after_residual)), _code(out), _stream(),
+          flops=2.0 * B * Ho * Wo * N * ks * ks * C, nbytes=_nbytes(x, w, out, residual))
     return out
 
 

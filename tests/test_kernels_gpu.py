@@ -595,3 +595,37 @@ def test_grouped_im2col_and_per_group_gemm_equal_grouped_conv(cg, stride):
                                      stride=stride, padding=1, groups=G).permute(0, 2, 3, 1).reshape(-1, C)
     assert (out.float() - ref).abs().max().item() < 2e-2 + 4e-3 * ref.abs().max().item()
 
+
+@pytest.mark.parametrize("B,H,W,C,N,ks,stride", [
+    (3, 14, 14, 64, 64, 3, 1),       # one 8x16 patch row is partial in both directions
+    (2, 56, 56, 64, 64, 3, 1),       # ResNet stage 1
+    (2, 56, 56, 128, 128, 3, 2),     # strided: TMA traversal stride 2
+    (3, 7, 7, 512, 512, 3, 1),       # 8x8 patches of two images per tile, odd batch (second image out of bounds)
+    (5, 14, 14, 256, 320, 3, 2),     # -> 7x7, N tail over 256-wide tiles
+    (2, 20, 33, 64, 72, 5, 1),       # other kernel size / odd sizes
+])
+@pytest.mark.parametrize("mode", ["plain", "residual"])
+def test_implicit_gemm_conv(B, H, W, C, N, ks, stride, mode):
+    """k x k convolution whose A tiles are 4-D TMA boxes of the NHWC input (zero padding = out-of-bounds fill)."""
+    ops = _ops()
+    pad = (ks - 1) // 2
+    g = torch.Generator(device="cuda").manual_seed(H * 7 + C + stride)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(ks, ks, C, N, device="cuda", generator=g) / (ks * math.sqrt(C))).to(torch.bfloat16)  # TF layout
+    bias = torch.randn(N, device="cuda", generator=g)
+    w2 = w.reshape(ks * ks * C, N).t().contiguous()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(3, 2, 0, 1), bias,
+                                     stride=stride, padding=pad).permute(0, 2, 3, 1)
+    if mode == "plain":
+        out = ops.conv_gemm(x, w2, bias=bias, ks=ks, stride=stride, pad=pad, act="relu")
+        ref = torch.relu(ref)
+    else:
+        res = torch.randn(ref.shape, device="cuda", generator=g)
+        out = ops.conv_gemm(x, w2, bias=bias, ks=ks, stride=stride, pad=pad, act="relu", residual=res,
+                            act_after_residual=True)
+        ref = torch.relu(ref + res)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape
+    tol = 3e-3 if out.dtype == torch.float32 else 2e-2 + 4e-3 * ref.abs().max().item()
+    assert (out.float() - ref).abs().max().item() < tol
+
