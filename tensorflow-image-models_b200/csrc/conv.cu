@@ -21,6 +21,9 @@ namespace tfimm {
 int dwconv_bias_act_pairs(const void* x, int dtype, const float* wgt, const float* bias, void* out, float* pool_sum,
                           int B, int H, int W, int C, int ks, int stride, int pad_t, int pad_l, int Ho, int Wo,
                           int act, cudaStream_t stream);
+int dwconv_bias_act_tma(const void* x, int dtype, const float* wgt, const float* bias, void* out, float* pool_sum,
+                        int B, int H, int W, int C, int ks, int stride, int pad_t, int pad_l, int Ho, int Wo, int act,
+                        cudaStream_t stream);
 int dwconv7_ln_cluster(const void* x, int in_dtype, const float* wgt, const float* bias, const float* gamma,
                        const float* beta, void* out, int out_dtype, int B, int H, int W, int C, float eps,
                        cudaStream_t stream);
@@ -262,10 +265,14 @@ __global__ void global_avg_pool_kernel(const T* __restrict__ x, float* __restric
 // out[g][(b, oy, ox)][(ky, kx, c)] = x[b, oy*s + ky - pad_t, ox*s + kx - pad_l, g*cg + c] (0 outside), c < cg = C / G,
 // columns padded with zeros to Kpad.  G = 1 is the plain im2col; column order == TF conv kernel (kh, kw, cin, :)
 // flattened.  G > 1 lays the groups of a grouped convolution out as G separate [M][Kpad] matrices, one GEMM each.
-template <typename InT, typename OutT>
-__global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out, int B, int H, int W, int C, int G,
-                              int Ho, int Wo, int ks, int stride, int pad_t, int pad_l, int Kpad) {
-  const int cg = C / G;
+// KS_T / C_T: compile-time kernel size and channel count for the RGB stems (7x7 and 3x3 on 3 channels), where the
+// per-element (tap, channel) decomposition would otherwise be runtime integer divisions; 0 = runtime values.
+template <typename InT, typename OutT, int KS_T = 0, int C_T = 0>
+__global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out, int B, int H, int W, int C_rt, int G,
+                              int Ho, int Wo, int ks_rt, int stride, int pad_t, int pad_l, int Kpad) {
+  const int C = C_T > 0 ? C_T : C_rt;
+  const int ks = KS_T > 0 ? KS_T : ks_rt;
+  const int cg = C_T > 0 ? C_T : C / G;
   const int K = ks * ks * cg;
   const int chunks = Kpad >> 3;
   const long M = (long)B * Ho * Wo;
@@ -427,7 +434,13 @@ int im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, 
 #define TFIMM_I2C(IN, OUT)                                                                              \
   im2col_kernel<IN, OUT><<<grid, 256, 0, stream>>>(reinterpret_cast<const IN*>(x), reinterpret_cast<OUT*>(out), \
                                                   B, H, W, C, groups, Ho, Wo, ks, stride, pad_t, pad_l, Kpad)
-  if (in_dtype == kF32 && out_dtype == kBF16) TFIMM_I2C(float, __nv_bfloat16);
+#define TFIMM_I2C_STEM(IN, OUT, KS_T)                                                                         \
+  im2col_kernel<IN, OUT, KS_T, 3><<<grid, 256, 0, stream>>>(reinterpret_cast<const IN*>(x), reinterpret_cast<OUT*>(out), \
+                                                           B, H, W, C, groups, Ho, Wo, ks, stride, pad_t, pad_l, Kpad)
+  if (C == 3 && groups == 1 && (ks == 7 || ks == 3) && out_dtype == kBF16 && (in_dtype == kF32 || in_dtype == kBF16)) {
+    if (in_dtype == kF32) { if (ks == 7) TFIMM_I2C_STEM(float, __nv_bfloat16, 7); else TFIMM_I2C_STEM(float, __nv_bfloat16, 3); }
+    else { if (ks == 7) TFIMM_I2C_STEM(__nv_bfloat16, __nv_bfloat16, 7); else TFIMM_I2C_STEM(__nv_bfloat16, __nv_bfloat16, 3); }
+  } else if (in_dtype == kF32 && out_dtype == kBF16) TFIMM_I2C(float, __nv_bfloat16);
   else if (in_dtype == kBF16 && out_dtype == kBF16) TFIMM_I2C(__nv_bfloat16, __nv_bfloat16);
   else if (in_dtype == kF32 && out_dtype == kF32) TFIMM_I2C(float, float);
   else {
@@ -435,6 +448,7 @@ int im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, 
     return kInvalidArgument;
   }
 #undef TFIMM_I2C
+#undef TFIMM_I2C_STEM
   TFIMM_LAUNCH_OK("im2col_kernel");
   return kOk;
 }
@@ -550,8 +564,21 @@ int dwconv_bias_act(const void* x, int dtype, const float* wgt, const float* bia
                   "dwconv: kernel size 3/5/7 and stride 1/2 are instantiated (got k=%d s=%d)", ks, stride);
   TFIMM_CHECK_ARG(dtype == kBF16 || dtype == kF32, "dwconv: dtype must be bf16 or f32");
   {
-    // channel-pair / register-prefetch kernel (dwconv_act_sm100.cu) for k in {3,5}; the kernel below is the
-    // generic fallback (k = 7).
+    // bf16, k in {3,5}: TMA-halo shared-memory kernel (dwconv_act_tma_sm100.cu); TFIMM_B200_DWCONV_ACT=pairs
+    // selects the previous register-window kernel for A/B measurements
+    static const bool use_tma = [] {
+      const char* e = getenv("TFIMM_B200_DWCONV_ACT");
+      return e == nullptr || e[0] != 'p';
+    }();
+    if (use_tma) {
+      const int st = dwconv_bias_act_tma(x, dtype, wgt, bias, out, pool_sum, B, H, W, C, ks, stride, pad_t, pad_l, Ho,
+                                         Wo, act, stream);
+      if (st != kUnsupported) return st;
+    }
+  }
+  {
+    // channel-pair / register-prefetch kernel (dwconv_act_sm100.cu) for k in {3,5}, fp32 and odd shapes; the kernel
+    // below is the generic fallback (k = 7).
     const int st = dwconv_bias_act_pairs(x, dtype, wgt, bias, out, pool_sum, B, H, W, C, ks, stride, pad_t, pad_l,
                                          Ho, Wo, act, stream);
     if (st != kUnsupported) return st;

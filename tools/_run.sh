@@ -1,12 +1,13 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "implicit_gemm_conv or gemm_bf16" 2>&1 | tail -12
-timeout 600 python -m pytest tests/test_models_gpu.py -m gpu -x -q -k "resnet" 2>&1 | tail -4
-for c in implicit im2col; do
-TFIMM_B200_CONV=$c timeout 600 python bench.py --model resnet50 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_resnet50_$c.json 2> gpurun_out/bench_resnet50_$c.err
-tail -2 gpurun_out/bench_resnet50_$c.err
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "dwconv_bias_act or im2col" 2>&1 | tail -5
+for m in tma pairs; do TFIMM_B200_DWCONV_ACT=$m python tools/prof_kernels.py dwconv_act | tail -1; done
+timeout 600 python -m pytest tests/test_models_gpu.py -m gpu -x -q -k "efficientnet" 2>&1 | tail -3
+for m in efficientnet_b4 resnet50; do
+timeout 600 python bench.py --model $m --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_$m.json 2> gpurun_out/bench_$m.err
+tail -2 gpurun_out/bench_$m.err
 python - <<PY
 import json
-d=json.loads(open("gpurun_out/bench_resnet50_$c.json").read().strip().splitlines()[-1])
-print("$c", round(d["value"]), round(d["ms_per_step"],2), d["roofline"]["families_ms"])
+d=json.loads(open("gpurun_out/bench_$m.json").read().strip().splitlines()[-1])
+print("$m", round(d["value"]), round(d["ms_per_step"],2), d["roofline"]["families_ms"])
 PY
 done
