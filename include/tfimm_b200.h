@@ -196,7 +196,8 @@ int tfimm_b200_blur_pool(const void* x, int dtype, void* out, int B, int H, int 
 
 /* SqueezeExcite gate from pooled sums: gate[b] = gate_act(W_e act(W_r mean[b] + b_r) + b_e), fp32.
  * efficientnet_blocks.py:241-247 (mean -> conv_reduce -> act1 -> conv_expand -> gate), layers/attention.py:67-75.
- * w_reduce:[rd][C], w_expand:[C][rd]. */
+ * w_reduce:[rd][C] (the TF kernel (1,1,C,rd) transposed), w_expand:[rd][C] (the TF kernel (1,1,rd,C) as is: the
+ * expand loop then reads it coalesced across channels). */
 int tfimm_b200_se_gate(const float* pooled_sum, float inv_hw, const float* w_reduce, const float* b_reduce,
                        const float* w_expand, const float* b_expand, float* gate, int B, int C, int rd, int act,
                        int gate_act, void* stream);

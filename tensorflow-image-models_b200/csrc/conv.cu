@@ -322,7 +322,7 @@ __global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out,
 // ----------------------------------------------------------------------------------------------
 // squeeze-excite gate: pooled sums -> 1x1 conv (bias) -> act -> 1x1 conv (bias) -> gate act
 // ----------------------------------------------------------------------------------------------
-// One CTA per image.  pooled_sum[b][C] (sum over pixels), w_reduce[rd][C], w_expand[C][rd], fp32.
+// One CTA per image.  pooled_sum[b][C] (sum over pixels), w_reduce[rd][C], w_expand[rd][C], fp32.
 __global__ void se_gate_kernel(const float* __restrict__ pooled_sum, float inv_hw,
                                const float* __restrict__ w_reduce, const float* __restrict__ b_reduce,
                                const float* __restrict__ w_expand, const float* __restrict__ b_expand,
@@ -335,16 +335,29 @@ __global__ void se_gate_kernel(const float* __restrict__ pooled_sum, float inv_h
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   for (int r = warp; r < rd; r += warps) {
-    float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(mean[c], w_reduce[(long)r * C + c], acc);
-    acc = warp_sum(acc);
+    float acc = 0.f, acc1 = 0.f;
+    int c = lane;
+    for (; c + 32 < C; c += 64) {
+      acc = fmaf(mean[c], __ldg(w_reduce + (long)r * C + c), acc);
+      acc1 = fmaf(mean[c + 32], __ldg(w_reduce + (long)r * C + c + 32), acc1);
+    }
+    if (c < C) acc = fmaf(mean[c], __ldg(w_reduce + (long)r * C + c), acc);
+    acc = warp_sum(acc + acc1);
     if (lane == 0) hid[r] = apply_act<true>(acc + b_reduce[r], act);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = b_expand[c];
-    for (int r = 0; r < rd; ++r) acc = fmaf(hid[r], w_expand[(long)c * rd + r], acc);
-    gate[(long)b * C + c] = apply_act<true>(acc, gate_act);
+    // w_expand is [rd][C]: consecutive threads read consecutive channels (coalesced); 4 independent chains
+    float a0 = b_expand[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int r = 0;
+    for (; r + 4 <= rd; r += 4) {
+      a0 = fmaf(hid[r], __ldg(w_expand + (long)r * C + c), a0);
+      a1 = fmaf(hid[r + 1], __ldg(w_expand + (long)(r + 1) * C + c), a1);
+      a2 = fmaf(hid[r + 2], __ldg(w_expand + (long)(r + 2) * C + c), a2);
+      a3 = fmaf(hid[r + 3], __ldg(w_expand + (long)(r + 3) * C + c), a3);
+    }
+    for (; r < rd; ++r) a0 = fmaf(hid[r], __ldg(w_expand + (long)r * C + c), a0);
+    gate[(long)b * C + c] = apply_act<true>((a0 + a1) + (a2 + a3), gate_act);
   }
 }
 

@@ -271,7 +271,7 @@ class EfficientNet(Model):
 
     def _se_weights(self, prefix):
         wr = self.params[f"{prefix}/conv_reduce/kernel"].float()[0, 0].t().contiguous()   # (rd, C)
-        we = self.params[f"{prefix}/conv_expand/kernel"].float()[0, 0].t().contiguous()   # (C, rd)
+        we = self.params[f"{prefix}/conv_expand/kernel"].float()[0, 0].contiguous()       # (rd, C): TF layout as is
         return wr, self._vec(f"{prefix}/conv_reduce/bias"), we, self._vec(f"{prefix}/conv_expand/bias")
 
     def _compile(self):

@@ -277,7 +277,7 @@ class ResNet(Model):
                 d["conv3"] = self._folded_conv(f"{p}/conv3", f"{p}/bn3")
             if b.attn == "se":
                 d["se"] = (self.params[f"{p}/se/fc1/kernel"].float()[0, 0].t().contiguous(), self._vec(f"{p}/se/fc1/bias"),
-                           self.params[f"{p}/se/fc2/kernel"].float()[0, 0].t().contiguous(), self._vec(f"{p}/se/fc2/bias"))
+                           self.params[f"{p}/se/fc2/kernel"].float()[0, 0].contiguous(), self._vec(f"{p}/se/fc2/bias"))
             elif b.attn == "eca":
                 d["eca"] = self._vec(f"{p}/se/conv/kernel")
             if b.shortcut == "conv":

@@ -477,7 +477,7 @@ def test_se_gate_scale_and_eca():
     we = torch.randn(C, rd, device="cuda", generator=g) / rd ** 0.5
     be = torch.randn(C, device="cuda", generator=g)
     pooled_sum = x.sum(dim=(1, 2)).contiguous()
-    gate = ops.se_gate(pooled_sum, H * W, wr, br, we, be, act="swish")
+    gate = ops.se_gate(pooled_sum, H * W, wr, br, we.t().contiguous(), be, act="swish")  # expand weights as [rd][C]
     torch.cuda.synchronize()
     m = x.mean(dim=(1, 2))
     hdn = m @ wr.t() + br

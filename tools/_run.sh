@@ -1,8 +1,7 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "dwconv_bias_act or im2col" 2>&1 | tail -5
-for m in tma pairs; do TFIMM_B200_DWCONV_ACT=$m python tools/prof_kernels.py dwconv_act | tail -1; done
-timeout 600 python -m pytest tests/test_models_gpu.py -m gpu -x -q -k "efficientnet" 2>&1 | tail -3
-for m in efficientnet_b4 resnet50; do
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "se_gate" 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_models_gpu.py -m gpu -x -q -k "efficientnet or resnet" 2>&1 | tail -3
+for m in efficientnet_b4; do
 timeout 600 python bench.py --model $m --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_$m.json 2> gpurun_out/bench_$m.err
 tail -2 gpurun_out/bench_$m.err
 python - <<PY
