@@ -332,7 +332,11 @@ def run_b200(args):
                                    f"fp32 synthetic images, random-init weights, bf16 operands / fp32 accumulate "
                                    f"and residual stream",
                        "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
-                       "l2": "per-step working set (154 MB input + >1 GB activations) exceeds the 126 MB L2"},
+                       "l2": "per-step working set (154 MB input + >1 GB activations) exceeds the 126 MB L2",
+                       "graph_level": ("ViT last block: attention/proj/MLP evaluated for the class-token rows only "
+                                       "(the other rows cannot reach the logits); TFIMM_B200_VIT_PRUNE=0 disables"
+                                       if args.model.startswith(("vit", "deit")) and
+                                       os.environ.get("TFIMM_B200_VIT_PRUNE", "1") != "0" else "none")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d_bytes, "input": str(e2e_dtype).replace("torch.", ""),
                     "pipeline": "tfimm.serving.InferencePipeline depth 2 (H2D of step i+1 overlaps forward of step i)",

@@ -122,6 +122,13 @@ int tfimm_b200_patch_merge_ln(const void* x, int in_dtype, const float* gamma, c
  * [q|k|v] each head-major; out (B*N, H*dh).  tfimm/architectures/vit.py:149-165. bf16, dh == 64. */
 int tfimm_b200_attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
 
+/* Attention for the first nq query tokens only (class / distillation tokens) against all N keys: the attention core
+ * of the LAST ViT block, whose other query rows cannot reach the logits (ViT.forward_features keeps token 0, or
+ * tokens 0..1 for distilled models: tfimm/architectures/vit.py:452-464).  qkv: bf16 [B*N][3*H*64] (same packing as
+ * tfimm_b200_attention_bf16); out: bf16 [B*nq][H*64]. */
+int tfimm_b200_attention_cls_bf16(const void* qkv, void* out, int B, int N, int H, int head_dim, int nq, float scale,
+                                  void* stream);
+
 /* fp32 attention with optional additive bias[H,N,N] and mask[nmask,N,N] (window b uses mask b % nmask)
  * and optional probability output probs[B,H,N,N] (features["attn"], vit.py:163).
  * row_map (optional, int32[nw_img*N]): window b reads/writes image (b / nw_img), token

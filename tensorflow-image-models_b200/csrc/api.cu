@@ -43,6 +43,7 @@ int gemm_bf16_dispatch(const void*, int, const void*, int, const float*, const f
                        int, int, int, int, int, int, int, int, const float*, int, const float*, float, void*, int,
                        float*, int, cudaStream_t);
 int gemm_bf16_stat_parts(int, int, int);
+int attention_cls_bf16(const void*, void*, int, int, int, int, int, float, cudaStream_t);
 int conv_bf16_dispatch(const void*, const void*, int, const float*, const void*, void*, int, int, int, int, int, int,
                        int, int, int, int, int, cudaStream_t);
 int row_stats_cast(const float*, long, void*, long, float*, long, int, cudaStream_t);
@@ -116,6 +117,11 @@ int tfimm_b200_conv_bf16(const void* x, const void* W, int ldw, const float* bia
                          int act_after_residual, int out_dtype, void* stream) {
   return tfimm::conv_bf16_dispatch(x, W, ldw, bias, residual, out, B, H, Wd, C, N, ks, stride, pad, act,
                                    act_after_residual, out_dtype, S(stream));
+}
+
+int tfimm_b200_attention_cls_bf16(const void* qkv, void* out, int B, int N, int H, int head_dim, int nq, float scale,
+                                  void* stream) {
+  return tfimm::attention_cls_bf16(qkv, out, B, N, H, head_dim, nq, scale, S(stream));
 }
 
 int tfimm_b200_gemm_stat_parts(int M, int N, int force_block_n) {

@@ -223,6 +223,8 @@ class ViT(Model):
             # (sum, sumsq) statistics, both refreshed by the epilogue of every GEMM that updates the stream
             x16, st = ops.row_stats_cast(xs)
             st_blk = torch.empty((B * T, ops.gemm_stat_parts(B * T, D), 2), device=xs.device, dtype=torch.float32)
+        prune_last = (not return_features and self.precision == "bf16" and dh == 64 and T <= 512
+                      and os.environ.get("TFIMM_B200_VIT_PRUNE", "1") != "0")
         for j, blk in enumerate(P["blocks"]):
             if fold:
                 wf, cs, bf = blk["qkv_ln"]
@@ -234,6 +236,20 @@ class ViT(Model):
                 probs = torch.empty((B, Hh, T, T), device=xs.device, dtype=torch.float32)
                 ops.attention(ops.cast(qkv, torch.float32), B, T, Hh, dh, scale, probs=probs)
                 features[f"block_{j}/attn"] = probs
+            if prune_last and j == len(P["blocks"]) - 1:
+                # Last block: only the class (and distillation) token rows reach the head (vit.py:452-464), so
+                # attention, proj, norm2 and the MLP run on those B * nq rows only; keys / values above came from
+                # every token.  Same arithmetic per row, 6-7 % of a ViT-B step.  TFIMM_B200_VIT_PRUNE=0 disables.
+                nq = 2 if c.distilled else 1
+                a = ops.attention_cls(qkv, B, T, Hh, dh, scale, nq)
+                x3 = xs.view(B, T, D)
+                for i in range(nq):
+                    xi = x3[:, i]                                   # (B, D) view of the fp32 stream, row stride T*D
+                    ops.gemm(a.view(B, nq, D)[:, i], blk["proj_w"], bias=blk["proj_b"], residual=xi, out=xi)
+                    hi = ops.layernorm(xi, *blk["n2"], eps, adt)
+                    hid = ops.gemm(hi, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)
+                    ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], residual=xi, out=xi)
+                continue
             a = ops.attention(qkv, B, T, Hh, dh, scale)
             if fold:
                 st = st_blk

@@ -166,6 +166,16 @@ def conv_gemm(x, w, bias=None, ks=3, stride=1, pad=1, act=None, residual=None, a
     return out
 
 
+def attention_cls(qkv, B, T, H, dh, scale, nq=1):
+    """softmax(q K^T) V for the first ``nq`` query tokens of every image only -> (B*nq, H*dh) bf16."""
+    _cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * T, 3 * H * dh)
+    out = torch.empty((B * nq, H * dh), device=qkv.device, dtype=torch.bfloat16)
+    _call("tfimm_b200_attention_cls_bf16", qkv.data_ptr(), out.data_ptr(), B, T, H, dh, nq, float(scale), _stream(),
+          flops=4.0 * B * H * nq * T * dh, nbytes=2.0 * B * T * 2 * H * dh)
+    return out
+
+
 def layernorm(x, gamma, beta, eps, out_dtype, out=None):
     """LayerNorm over the last axis of a 2D (possibly row-strided) tensor."""
     _cuda(x, gamma, beta, out)

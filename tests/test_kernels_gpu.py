@@ -269,6 +269,20 @@ def _attn_ref(qkv, B, N, H, dh, scale, bias=None, mask=None):
     return o, p
 
 
+@pytest.mark.parametrize("B,N,H,nq", [(3, 197, 12, 1), (2, 198, 3, 2), (5, 50, 6, 1), (1, 512, 2, 2)])
+def test_attention_cls_rows_equal_full_attention(B, N, H, nq):
+    ops = _ops()
+    dh = 64
+    g = torch.Generator(device="cuda").manual_seed(N + nq)
+    qkv = (torch.randn(B * N, 3 * H * dh, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    out = ops.attention_cls(qkv, B, N, H, dh, dh ** -0.5, nq)
+    torch.cuda.synchronize()
+    ref, _ = _attn_ref(qkv, B, N, H, dh, dh ** -0.5)
+    ref = ref.view(B, N, H * dh)[:, :nq].reshape(B * nq, H * dh)
+    assert out.shape == ref.shape
+    assert (out.float() - ref).abs().max().item() < 1.5e-2   # fp32 math, one bf16 output rounding
+
+
 @pytest.mark.parametrize("B,N,H", [(2, 197, 12), (3, 5, 2), (1, 65, 3), (2, 128, 4), (1, 224, 2), (1, 577, 2), (2, 17, 1)])
 def test_attention_bf16(B, N, H):
     ops = _ops()
