@@ -559,8 +559,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Relaxed: callers order their own accesses (tcgen05.fence::before_thread_sync for TMEM reads).  The default
+// .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR, which was 15 % of the epilogue warps' time in the
+// CTA-pair GEMM (ncu source view, profiles/r01_ncu_full_gemm_fc1_pair.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_arrive_release() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");

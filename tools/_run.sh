@@ -1,12 +1,10 @@
-mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "attention" 2>&1 | tail -3
-timeout 600 python -m pytest tests/test_models_gpu.py -m gpu -x -q -k "vit or deit or golden or graph or uint8 or pipeline" 2>&1 | tail -3
-for pr in 1 0; do
-TFIMM_B200_VIT_PRUNE=$pr timeout 600 python bench.py --model vit_base_patch16_224 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_vit_prune$pr.json 2> gpurun_out/bench_vit_prune$pr.err
-tail -2 gpurun_out/bench_vit_prune$pr.err
-python - <<PY
-import json
-d=json.loads(open("gpurun_out/bench_vit_prune$pr.json").read().strip().splitlines()[-1])
-print("prune=$pr", round(d["value"]), round(d["ms_per_step"],2), d["roofline"]["families_ms"], d["clocks"]["sm_mhz"], d["gpu_launches"]//25)
-PY
-done
+for rep in 1 2; do
+for lib in /root/repo/gpurun_libA.so /root/repo/tensorflow-image-models_b200/tfimm/backend/libtfimm_b200.so; do
+echo "== $lib"
+TFIMM_B200_LIB=$lib python tools/bench_gemm.py 50432 3072 768 gelu bf16 0 2 | tail -1
+TFIMM_B200_LIB=$lib python tools/bench_gemm.py 50432 3072 768 none bf16 0 2 | tail -1
+TFIMM_B200_LIB=$lib python tools/bench_gemm.py 50432 2304 768 none bf16 0 2 | tail -1
+TFIMM_B200_LIB=$lib python tools/bench_gemm.py 50432 768 3072 none f32 1 2 | tail -1
+TFIMM_B200_LIB=$lib python tools/bench_gemm.py 50176 2048 512 gelu bf16 0 2 | tail -1
+done; done
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "gemm" 2>&1 | tail -2
