@@ -10,10 +10,14 @@
 //   * all TMA completions are credited to the LEADER CTA's "full" barrier; the leader's MMA warp issues the
 //     pair-wide MMAs; tcgen05.commit multicasts the "slot free" and "accumulator ready" arrivals to both CTAs
 //   * each CTA's TMEM holds its 128 rows x 256 columns of the fp32 accumulator (two stages: 512 columns); the
-//     eight epilogue warps of each CTA drain their own half exactly as in the one-CTA kernel and release the
-//     accumulator stage with a remote arrive on the leader's barrier
-// Warp roles per CTA (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader only) + TMEM alloc,
-// warps 2..9 epilogue.  Pairs are persistent over the tile list.
+//     epilogue warps of each CTA drain their own half (same code as the one-CTA kernel) and release the
+//     accumulator stage with a relaxed remote arrive on the leader's barrier
+//   * bf16 output (qkv, fc1 + GELU: the instances whose tile time is set by the EPILOGUE, not the tensor pipe, when
+//     K <= 768): SIXTEEN epilogue warps, four per SM sub-partition, on 32-column chunks (64-byte rows, 2 KB slabs,
+//     64B-swizzled TMA stores) so that two loads / activations / stores are in flight per sub-partition scheduler
+//     and each warp's registers stay under the 576-thread budget.  fp32 output (residual GEMMs): eight warps.
+// Warp roles per CTA: warp 0 TMA producer, warp 1 MMA issuer (leader only) + TMEM alloc, warps 2.. epilogue.
+// Pairs are persistent over the tile list.
 #include "gemm_epilogue.cuh"
 
 namespace tfimm {
@@ -25,41 +29,52 @@ constexpr int kBlockN = 256;   // UMMA N
 constexpr int kHalfN = 128;    // W rows loaded by each CTA
 constexpr int kBlockK = 64;    // 64 bf16 = one 128-byte swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kNumEpiWarps = 8;
-constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
 constexpr int kAccStages = 2;
-constexpr int kStages = 5;
 constexpr int kABytes = kCtaM * kBlockK * 2;
 constexpr int kBBytes = kHalfN * kBlockK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;  // per CTA
-constexpr int kSlabTotal = kNumEpiWarps * (kEpiSlabBytes + kEpiCopySlabBytes);  // output slabs, then bf16-copy slabs
-constexpr int kNumBarriers = 2 * kStages + 2 * kAccStages + kNumEpiWarps;
-constexpr int kSmemBytes = kStages * kStageBytes + kSlabTotal + kNumBarriers * 8 + 16 + 1024 /*alignment slack*/;
 constexpr uint32_t kTmemCols = kAccStages * kBlockN;  // 512: all of this SM's tensor memory
-static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+constexpr int kCH = 32;        // output columns per epilogue chunk (both output types)
 
 template <typename OutT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+struct PairCfg {
+  static constexpr int kEpiGroups = sizeof(OutT) == 2 ? 4 : 2;  // epilogue warps per TMEM lane quarter
+  static constexpr int kNumEpiWarps = 4 * kEpiGroups;
+  static constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
+  static constexpr int kSlabBytes = 32 * kCH * (int)sizeof(OutT);                     // 2 KB (bf16) / 4 KB (fp32)
+  static constexpr int kCopySlabBytes = sizeof(OutT) == 4 ? kEpiCopySlabBytes : 0;    // bf16 copy (emit mode)
+  static constexpr int kSlabTotal = kNumEpiWarps * (kSlabBytes + kCopySlabBytes);
+  static constexpr int kStages = 5;
+  static constexpr int kNumBarriers = 2 * kStages + 2 * kAccStages + kNumEpiWarps;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabTotal + kNumBarriers * 8 + 16 + 1024 /*align*/;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+};
+
+template <typename OutT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<OutT>::kNumThreads, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                               const __grid_constant__ CUtensorMap tmap_b,
                               const __grid_constant__ CUtensorMap tmap_c,
                               const __grid_constant__ CUtensorMap tmap_r,
                               const __grid_constant__ CUtensorMap tmap_c2, const GemmParams p) {
-  constexpr int CH = 128 / (int)sizeof(OutT);  // output columns per 128-byte slab row
-  constexpr int NCH = kBlockN / CH;
+  using Cfg = PairCfg<OutT>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kNumEpiWarps = Cfg::kNumEpiWarps;
+  constexpr int kEpiGroups = Cfg::kEpiGroups;
+  constexpr int NCH = kBlockN / kCH;
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment (identical offsets in both CTAs: same kernel, same smem layout)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_tiles = smem_base;
   const uint32_t smem_slabs = smem_base + kStages * kStageBytes;
-  const uint32_t smem_bars = smem_slabs + kSlabTotal;
+  const uint32_t smem_bars = smem_slabs + Cfg::kSlabTotal;
   auto full_bar = [&](int s) { return smem_bars + 8u * s; };
   auto empty_bar = [&](int s) { return smem_bars + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return smem_bars + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return smem_bars + 8u * (2 * kStages + kAccStages + s); };
   auto res_bar = [&](int w) { return smem_bars + 8u * (2 * kStages + 2 * kAccStages + w); };
-  const uint32_t tmem_ptr_smem = smem_bars + 8u * kNumBarriers;
+  const uint32_t tmem_ptr_smem = smem_bars + 8u * Cfg::kNumBarriers;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of smem_base
 
   const int warp_idx = threadIdx.x >> 5;
@@ -155,12 +170,12 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else {
     // -------------------------------- epilogue (both CTAs) --------------------------------
-    const int ew = warp_idx - 2;         // 0..7: slab / residual-barrier owner
+    const int ew = warp_idx - 2;         // slab / residual-barrier owner
     const int q = warp_idx & 3;          // TMEM lane quarter this warp may access
-    const int grp = ew >> 2;             // which half of the column chunks this warp takes
-    const uint32_t slab = smem_slabs + (uint32_t)ew * kEpiSlabBytes;
-    uint8_t* my_row = smem_gen + (slab - smem_base) + lane * 128;
-    const uint32_t copy_slab = smem_slabs + kNumEpiWarps * kEpiSlabBytes + (uint32_t)ew * kEpiCopySlabBytes;
+    const int grp = ew >> 2;             // which share of the column chunks this warp takes
+    const uint32_t slab = smem_slabs + (uint32_t)ew * Cfg::kSlabBytes;
+    uint8_t* my_row = smem_gen + (slab - smem_base) + lane * (Cfg::kSlabBytes / 32);
+    const uint32_t copy_slab = smem_slabs + kNumEpiWarps * Cfg::kSlabBytes + (uint32_t)ew * Cfg::kCopySlabBytes;
     uint8_t* copy_row = smem_gen + (copy_slab - smem_base) + lane * 64;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -169,7 +184,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int m_blk = t / num_n_tiles, n_blk = t % num_n_tiles;
       const int row0 = m_blk * kPairM + (int)rank * kCtaM + q * 32;
       const int cols_left = p.N - n_blk * kBlockN;
-      const int nvalid = cols_left >= kBlockN ? NCH : (cols_left + CH - 1) / CH;
+      const int nvalid = cols_left >= kBlockN ? NCH : (cols_left + kCH - 1) / kCH;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * kBlockN) + ((uint32_t)(q * 32) << 16);
@@ -183,15 +198,16 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       float ln_rstd = 1.f, ln_nmr = 0.f, stat_s = 0.f, stat_q = 0.f;
       if (p.ln_stats != nullptr) ln_row_coeffs(p, row0 + lane, ln_rstd, ln_nmr);
 #pragma unroll 1
-      for (int c = grp; c < nvalid; c += 2) {
-        const int n0 = n_blk * kBlockN + c * CH;
-        const bool last = c + 2 >= nvalid;
-        epilogue_chunk<OutT>(p, t_acc + (uint32_t)(c * CH), n0, row0, slab, my_row, lane, res_bar(ew), cc & 1u,
-                             &tmap_c, &tmap_r, &tmap_c2, copy_slab, copy_row, ln_rstd, ln_nmr, stat_s, stat_q,
-                             /*ct=*/nullptr, [&]() { if (last) release_acc(); });
+      for (int c = grp; c < nvalid; c += kEpiGroups) {
+        const int n0 = n_blk * kBlockN + c * kCH;
+        const bool last = c + kEpiGroups >= nvalid;
+        epilogue_chunk<OutT, kCH>(p, t_acc + (uint32_t)(c * kCH), n0, row0, slab, my_row, lane, res_bar(ew), cc & 1u,
+                                  &tmap_c, &tmap_r, &tmap_c2, copy_slab, copy_row, ln_rstd, ln_nmr, stat_s, stat_q,
+                                  /*ct=*/nullptr, [&]() { if (last) release_acc(); });
         ++cc;
       }
-      if (p.emit_stats != nullptr) emit_row_stats(p, row0 + lane, 2 * n_blk + grp, 2 * num_n_tiles, stat_s, stat_q);
+      if (p.emit_stats != nullptr)
+        emit_row_stats(p, row0 + lane, kEpiGroups * n_blk + grp, kEpiGroups * num_n_tiles, stat_s, stat_q);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -210,16 +226,17 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
 template <typename OutT>
 int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const void* residual, int ldr, void* C, int ldc,
                      const GemmParams& p, cudaStream_t stream) {
+  using Cfg = PairCfg<OutT>;
   const int M = p.M, N = p.N, K = p.K;
   constexpr int out_dtype = sizeof(OutT) == 2 ? kBF16 : kF32;
-  constexpr int CH = 128 / (int)sizeof(OutT);
+  constexpr int row_bytes = kCH * (int)sizeof(OutT);  // 64 (bf16) or 128 (fp32): also the TMA swizzle span
   CUtensorMap ta, tb, tc, tr;
   int st;
   if ((st = make_tmap_2d(&ta, A, kBF16, M, K, lda, kCtaM, kBlockK, "A")) != kOk) return st;
   if ((st = make_tmap_2d(&tb, W, kBF16, N, K, ldw, kHalfN, kBlockK, "W")) != kOk) return st;
-  if ((st = make_tmap_2d(&tc, C, out_dtype, M, N, ldc, 32, CH, "C")) != kOk) return st;
+  if ((st = make_tmap_2d(&tc, C, out_dtype, M, N, ldc, 32, kCH, "C", row_bytes)) != kOk) return st;
   if (residual != nullptr) {
-    if ((st = make_tmap_2d(&tr, residual, out_dtype, M, N, ldr, 32, CH, "residual")) != kOk) return st;
+    if ((st = make_tmap_2d(&tr, residual, out_dtype, M, N, ldr, 32, kCH, "residual", row_bytes)) != kOk) return st;
   } else {
     tr = tc;
   }
@@ -230,18 +247,21 @@ int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const void*
   auto kernel = gemm_bf16_tcgen05_pair_kernel<OutT>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = ((M + kPairM - 1) / kPairM) * ((N + kBlockN - 1) / kBlockN);
   const int max_pairs = sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  kernel<<<2 * pairs, kNumThreads, kSmemBytes, stream>>>(ta, tb, tc, tr, tc2, p);
+  kernel<<<2 * pairs, Cfg::kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, tc2, p);
   TFIMM_LAUNCH_OK("gemm_bf16_tcgen05_pair_kernel");
   return kOk;
 }
 
 }  // namespace
+
+// Partial statistics per row a statistics-emitting launch of this kernel writes per 256-column tile.
+int gemm_bf16_pair_stat_groups(int out_dtype) { return out_dtype == kBF16 ? 4 : 2; }
 
 int gemm_bf16_pair(const void* A, int lda, const void* W, int ldw, const void* residual, int ldr, void* C, int ldc,
                    const GemmParams& p, int out_dtype, cudaStream_t stream) {

@@ -153,7 +153,9 @@ __device__ __forceinline__ void apply_act_pairs(uint64_t (&v)[NP], int act) {
 //   after_load called once the accumulator values are in registers (caller releases the TMEM stage there)
 //   ct         implicit-convolution mode: where this warp's 32 rows (a pw x 32/pw pixel patch of one image) sit
 //              in the NHWC output; null for a plain row-major C
-template <typename OutT, typename AfterLoad>
+//   CHW        columns per chunk: 128 bytes of output per row by default; the CTA-pair kernel's bf16 instance uses
+//              32 columns (64-byte rows, 64B swizzle, 2 KB slabs) so that sixteen epilogue warps fit
+template <typename OutT, int CHW = 128 / (int)sizeof(OutT), typename AfterLoad>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_addr, int n0, int row0,
                                                uint32_t slab, uint8_t* my_row, int lane, uint32_t res_bar,
                                                uint32_t res_parity, const CUtensorMap* tmap_c,
@@ -161,13 +163,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_a
                                                uint32_t copy_slab, uint8_t* copy_row, float ln_rstd, float ln_nmr,
                                                float& stat_s, float& stat_q, const ConvTile* ct,
                                                AfterLoad after_load) {
-  constexpr int CH = 128 / (int)sizeof(OutT);
-  const int sw = lane & 7;  // TMA SWIZZLE_128B: 16-byte chunk j of row r lives at j ^ (r & 7)
+  constexpr int CH = CHW;
+  constexpr int RB = CH * (int)sizeof(OutT);  // bytes per slab row: 128 or 64
+  constexpr int UNITS = RB / 16;
+  static_assert(RB == 128 || RB == 64, "slab rows are 128 or 64 bytes");
+  // TMA swizzle: 16-byte unit j of row r lives at j ^ (r & 7) (SWIZZLE_128B) or j ^ ((r >> 1) & 3) (SWIZZLE_64B)
+  const int sw = RB == 128 ? (lane & 7) : ((lane >> 1) & 3);
   // the previous store of this warp must have finished reading the slab
   if (lane == 0) {
     tma_store_wait_read<0>();
     if (p.has_res) {
-      mbar_expect_tx(res_bar, kEpiSlabBytes);
+      mbar_expect_tx(res_bar, 32 * RB);
       if (ct == nullptr) tma_load_2d(slab, tmap_r, res_bar, n0, row0);
       else tma_load_4d(slab, tmap_r, res_bar, n0, ct->x, ct->y, ct->b);
     }
@@ -193,7 +199,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_a
   if (p.has_res) {
     mbar_wait(res_bar, res_parity);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < UNITS; ++j) {
       const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
       if constexpr (sizeof(OutT) == 2) {
         const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
@@ -241,7 +247,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_a
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < UNITS; ++j) {
     uint4 u;
     if constexpr (sizeof(OutT) == 2) {
       float a0, a1, a2, a3, a4, a5, a6, a7;

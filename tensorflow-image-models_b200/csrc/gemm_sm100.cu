@@ -384,9 +384,11 @@ int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const flo
   if (emit_stats != nullptr) {
     const int ch = out_dtype == kBF16 ? 64 : 32;
     TFIMM_CHECK_ARG(N % ch == 0, "gemm: statistics emission needs N %% %d == 0 (got %d)", ch, N);
-    TFIMM_CHECK_ARG(emit_parts == 2 * ((N + bn - 1) / bn),
-                    "gemm: emit_parts must be %d for this shape (got %d); query tfimm_b200_gemm_stat_parts",
-                    2 * ((N + bn - 1) / bn), emit_parts);
+    // chunk groups per tile x N tiles (the CTA-pair kernel's bf16 instance runs four epilogue groups)
+    const int parts = (pair && out_dtype == kBF16 ? 4 : 2) * ((N + bn - 1) / bn);
+    TFIMM_CHECK_ARG(emit_parts == parts,
+                    "gemm: emit_parts must be %d for this shape (got %d); tfimm_b200_gemm_stat_parts gives the "
+                    "count for an fp32 C", parts, emit_parts);
     TFIMM_CHECK_ARG(emit_bf16 == nullptr || (out_dtype == kF32 && ld_emit % 8 == 0 &&
                                              (reinterpret_cast<uintptr_t>(emit_bf16) & 15u) == 0),
                     "gemm: the bf16 copy needs an fp32 C, ld_emit %% 8 == 0 and a 16-byte aligned pointer");
