@@ -36,6 +36,11 @@ def main(case):
         wt = torch.randn(49, 512, device="cuda", generator=g) / 7
         v = torch.randn(512, device="cuda", generator=g)
         fn = lambda: ops.dwconv_ln(x, wt, v, v, v, 1e-6, torch.bfloat16)
+    elif case == "dwconv_ln0":  # ConvNeXt-B stage 0
+        x = torch.randn(B, 56, 56, 128, device="cuda", generator=g)
+        wt = torch.randn(49, 128, device="cuda", generator=g) / 7
+        v = torch.randn(128, device="cuda", generator=g)
+        fn = lambda: ops.dwconv_ln(x, wt, v, v, v, 1e-6, torch.bfloat16)
     elif case == "window_attn":  # Swin-B stage 2, shifted
         from tfimm.architectures.swin import window_tables
 
