@@ -168,6 +168,15 @@ int tfimm_b200_dwconv_ln(const void* x, int in_dtype, const float* wgt, const fl
                          const float* beta, void* out, int out_dtype, int B, int H, int W, int C, int ks,
                          float eps, void* stream);
 
+/* ConvNeXt block head with the LayerNorm folded into the following Dense (tfimm/architectures/convnext.py:219-224):
+ * ZeroPadding2D(3) + DepthwiseConv2D(7, bias) only.  x: fp32 NHWC (the residual stream); out_bf16: the RAW convolution
+ * result, the A operand of tfimm_b200_gemm_bf16_ln; stats: [B*H*W][parts][2] per-pixel partial (sum, sum of squares)
+ * of the fp32 results, one pair per 64- (or 32-) channel slab, parts = tfimm_b200_dwconv7_stats_parts(C).
+ * No thread-block clusters, no LayerNorm passes: one 4-D TMA halo box per tile, FFMA2 taps, register stores. */
+int tfimm_b200_dwconv7_stats(const float* x, const float* wgt, const float* bias, void* out_bf16, float* stats, int B,
+                             int H, int W, int C, void* stream);
+int tfimm_b200_dwconv7_stats_parts(int C);
+
 /* DepthwiseConv2D(k in {3,5,7}, stride in {1,2}) with explicit top/left zero padding (covers TF "same"
  * and PadDepthwiseConv2D "symmetric", tfimm/layers/conv.py:91-148) + per-channel bias (folded BatchNorm)
  * + activation; optional fused squeeze: pool_sum[b][c] += sum over the output pixels (fp32 atomics; the

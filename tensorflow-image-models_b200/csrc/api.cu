@@ -43,6 +43,8 @@ int gemm_bf16_dispatch(const void*, int, const void*, int, const float*, const f
                        int, int, int, int, int, int, int, int, const float*, int, const float*, float, void*, int,
                        float*, int, cudaStream_t);
 int gemm_bf16_stat_parts(int, int, int);
+int dwconv7_stats(const void*, const float*, const float*, void*, float*, int, int, int, int, cudaStream_t);
+int dwconv7_stats_parts(int);
 int attention_cls_bf16(const void*, void*, int, int, int, int, int, float, cudaStream_t);
 int conv_bf16_dispatch(const void*, const void*, int, const float*, const void*, void*, int, int, int, int, int, int,
                        int, int, int, int, int, cudaStream_t);
@@ -123,6 +125,13 @@ int tfimm_b200_attention_cls_bf16(const void* qkv, void* out, int B, int N, int 
                                   void* stream) {
   return tfimm::attention_cls_bf16(qkv, out, B, N, H, head_dim, nq, scale, S(stream));
 }
+
+int tfimm_b200_dwconv7_stats(const float* x, const float* wgt, const float* bias, void* out_bf16, float* stats, int B,
+                             int H, int W, int C, void* stream) {
+  return tfimm::dwconv7_stats(x, wgt, bias, out_bf16, stats, B, H, W, C, S(stream));
+}
+
+int tfimm_b200_dwconv7_stats_parts(int C) { return tfimm::dwconv7_stats_parts(C); }
 
 int tfimm_b200_gemm_stat_parts(int M, int N, int force_block_n) {
   return tfimm::gemm_bf16_stat_parts(M, N, force_block_n);

@@ -53,7 +53,7 @@ def _call(name, *args, flops=0.0, nbytes=0.0):
         e0.record()
         _lib.check(fn(*args), name)
         e1.record()
-        trace.append((name.replace("tfimm_b200_", "").replace("gemm_bf16_ln", "gemm_bf16").replace("conv_bf16", "gemm_bf16"), e0, e1, float(flops),
+        trace.append((name.replace("tfimm_b200_", "").replace("gemm_bf16_ln", "gemm_bf16").replace("conv_bf16", "gemm_bf16").replace("dwconv7_stats", "dwconv_ln"), e0, e1, float(flops),
                       float(nbytes)))
     else:
         _lib.check(fn(*args), name)
@@ -174,6 +174,22 @@ def attention_cls(qkv, B, T, H, dh, scale, nq=1):
     _call("tfimm_b200_attention_cls_bf16", qkv.data_ptr(), out.data_ptr(), B, T, H, dh, nq, float(scale), _stream(),
           flops=4.0 * B * H * nq * T * dh, nbytes=2.0 * B * T * 2 * H * dh)
     return out
+
+
+def dwconv7_stats(x, wgt, bias):
+    """ZeroPad(3) + depthwise 7x7 + bias of an fp32 NHWC tensor -> (raw result bf16 (B,H,W,C), per-pixel partial
+    (sum, sumsq) statistics (B*H*W, parts, 2) fp32) for a LayerNorm-folded GEMM."""
+    _cuda(x, wgt, bias)
+    B, H, W, C = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and wgt.shape == (49, C)
+    parts = int(_lib.load().tfimm_b200_dwconv7_stats_parts(C))
+    if parts <= 0:
+        raise ValueError(f"dwconv7_stats needs C % 32 == 0 (C={C})")
+    out = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
+    stats = torch.empty((B * H * W, parts, 2), device=x.device, dtype=torch.float32)
+    _call("tfimm_b200_dwconv7_stats", x.data_ptr(), wgt.data_ptr(), bias.data_ptr(), out.data_ptr(), stats.data_ptr(),
+          B, H, W, C, _stream(), flops=2.0 * 49 * x.numel(), nbytes=_nbytes(x, out, stats))
+    return out, stats
 
 
 def layernorm(x, gamma, beta, eps, out_dtype, out=None):

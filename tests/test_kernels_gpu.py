@@ -358,6 +358,37 @@ def test_dwconv7x7_ln(C, H, W, in_dtype, out_dtype):
     _check_dwconv7x7_ln(C, H, W, in_dtype, out_dtype, B=2)
 
 
+@pytest.mark.parametrize("C,H,W,B", [(128, 56, 56, 2), (512, 14, 14, 48), (1024, 7, 7, 5), (96, 9, 13, 3), (192, 5, 3, 2)])
+def test_dwconv7x7_stats_then_layernorm_folded_gemm(C, H, W, B):
+    """ConvNeXt block head as two launches: depthwise 7x7 emitting the raw bf16 result + per-pixel partial
+    statistics, then the LayerNorm-folded GEMM -- against conv -> LayerNorm -> Dense in fp32."""
+    ops = _ops()
+    N, eps = 2 * C, 1e-6
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g)
+    wgt = torch.randn(49, C, device="cuda", generator=g) / 7
+    bias = torch.randn(C, device="cuda", generator=g)
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(C, device="cuda", generator=g)
+    w1 = torch.randn(N, C, device="cuda", generator=g) / math.sqrt(C)
+    b1 = torch.randn(N, device="cuda", generator=g)
+    raw, stats = ops.dwconv7_stats(x, wgt, bias)
+    torch.cuda.synchronize()
+    wt = wgt.view(7, 7, C).permute(2, 0, 1)[:, None]
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), wt, bias, padding=3, groups=C).permute(0, 2, 3, 1)
+    assert (raw.float() - y).abs().max().item() <= 2.0 ** -8 * y.abs().max().item() + 1e-3
+    y2 = y.reshape(-1, C)
+    assert (stats[:, :, 0].sum(1) - y2.sum(1)).abs().max().item() < 2e-3 * max(1.0, C / 128)
+    assert ((stats[:, :, 1].sum(1) - (y2 * y2).sum(1)).abs() / (y2 * y2).sum(1)).max().item() < 1e-4
+    wf = (w1 * gamma[None, :]).to(torch.bfloat16)
+    out = ops.gemm(raw.view(-1, C), wf, bias=(b1 + w1 @ beta).contiguous(), act="gelu",
+                   ln=(stats, wf.float().sum(1).contiguous(), eps), out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(y2, (C,), gamma, beta, eps) @ w1.t() + b1)
+    err = (out - ref).abs().max().item()
+    assert err < 3e-2 + 6e-3 * ref.abs().max().item(), err
+
+
 @pytest.mark.parametrize("C,H,W,B", [(512, 14, 14, 48), (1024, 7, 7, 64), (128, 28, 28, 24), (96, 14, 14, 40)])
 def test_dwconv7x7_ln_many_tiles(C, H, W, B):
     # more tiles than co-resident clusters: the persistent clusters loop, re-using halo / stash / mbarrier phases
