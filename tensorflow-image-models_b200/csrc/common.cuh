@@ -168,12 +168,18 @@ __device__ __forceinline__ uint64_t gelu_poly2(uint64_t x) {
   p = fma2(p, t, splat2(3.97883340e-01f));
   return mul2(x, fma2(xc, p, splat2(0.5f)));
 }
+// swish(x) = x * sigmoid(x) = x * (0.5 * tanh(x / 2) + 0.5): ONE MUFU op per element (tanh.approx, rel. error 2^-11)
+// instead of ex2 + rcp -- the swish epilogues of the MBConv GEMMs / depthwise kernels are MUFU-throughput bound
+// (16 MUFU lanes per SM per clock).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint64_t swish_fast2(uint64_t x) {
-  float z0, z1;
-  unpack2(mul2(x, splat2(-1.4426950408889634f)), z0, z1);
-  float d0, d1;
-  unpack2(add2(pack2(ex2_approx(z0), ex2_approx(z1)), splat2(1.0f)), d0, d1);
-  return mul2(x, pack2(rcp_approx(d0), rcp_approx(d1)));
+  float h0, h1;
+  unpack2(mul2(x, splat2(0.5f)), h0, h1);
+  return mul2(x, fma2(pack2(tanh_approx(h0), tanh_approx(h1)), splat2(0.5f), splat2(0.5f)));
 }
 
 template <bool kPrecise>

@@ -148,6 +148,17 @@ def test_convnext_bf16_parity(name):
     assert rel < BF16_TOL
 
 
+@pytest.mark.parametrize("name", ["convnext_tiny", "convnext_base"])
+def test_convnext_bf16_parity_with_folded_layernorm(name, monkeypatch):
+    """Opt-in path: cluster-free depthwise kernel + statistics, LayerNorm folded into fc1 (convnext_tiny: 32-channel
+    slabs, convnext_base: 64-channel slabs)."""
+    monkeypatch.setenv("TFIMM_B200_CONVNEXT_FOLD", "1")
+    _, _, _, out, ref = _run(name, "convnext", "bf16", 2)
+    rel, ab = _nerr(out, ref)
+    print(f"{name} bf16 (LN folded): normalised {rel:.3e} abs {ab:.3e}")
+    assert rel < BF16_TOL
+
+
 def test_convnext_return_features():
     import tfimm
     from oracle import convnext as oc
