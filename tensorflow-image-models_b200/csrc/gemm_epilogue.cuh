@@ -127,7 +127,7 @@ __device__ __forceinline__ void apply_act_pairs(uint64_t (&v)[NP], int act) {
   switch (act) {
     case kActGelu:
 #pragma unroll
-      for (int j = 0; j < NP; ++j) v[j] = gelu_poly2(v[j]);
+      for (int j = 0; j < NP; ++j) v[j] = gelu_tanh2(v[j]);
       break;
     case kActSwish:
 #pragma unroll
