@@ -130,44 +130,6 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   return d;
 }
 
-// gelu_fast on a pair: same formula, FMA-pipe work halved by FFMA2 (MUFU rcp/ex2 stay scalar).
-__device__ __forceinline__ uint64_t gelu_fast2(uint64_t x) {
-  float x0, x1;
-  unpack2(x, x0, x1);
-  const uint64_t ax = pack2(fabsf(x0), fabsf(x1));
-  float u0, u1;
-  unpack2(fma2(ax, splat2(0.3275911f * 0.70710678f), splat2(1.0f)), u0, u1);
-  const uint64_t t = pack2(rcp_approx(u0), rcp_approx(u1));
-  uint64_t p = fma2(splat2(0.5f * 1.061405429f), t, splat2(0.5f * -1.453152027f));
-  p = fma2(p, t, splat2(0.5f * 1.421413741f));
-  p = fma2(p, t, splat2(0.5f * -0.284496736f));
-  p = fma2(p, t, splat2(0.5f * 0.254829592f));
-  p = mul2(p, t);  // 0.5 * erfc(|x|/sqrt2) * exp(x^2/2)
-  float z0, z1;
-  unpack2(mul2(mul2(ax, splat2(-0.72134752044448170368f)), ax), z0, z1);
-  const uint64_t e = pack2(ex2_approx(z0), ex2_approx(z1));
-  const uint64_t h = mul2(mul2(p, e), ax);  // |x| * Phi(-|x|)
-  // gelu(x) = relu(x) - h
-  return fma2(h, splat2(-1.0f), pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
-}
-// GELU (erf form) without MUFU: x * Phi(x), Phi(x) = 1/2 + xc * P(xc^2), xc = clamp(x, -4, 4), P a degree-6
-// minimax fit of (Phi(x) - 1/2) / x on [0, 4] (weighted for the error of x * Phi).  |abs error| < 2e-4 for all x
-// (relative 4e-5 |x| beyond the clamp), i.e. well below one bf16 ulp of the GEMM outputs it is applied to.
-// 9 packed FMA-pipe instructions + 4 FMNMX per PAIR (gelu_fast2: 11 + 4 ALU + 4 MUFU): the epilogue of the
-// K = 768 GEMMs is instruction/MUFU bound (profiles/r01_ncu_full_gemm_fc1.txt), not tensor bound.
-__device__ __forceinline__ uint64_t gelu_poly2(uint64_t x) {
-  float x0, x1;
-  unpack2(x, x0, x1);
-  const uint64_t xc = pack2(fminf(fmaxf(x0, -4.0f), 4.0f), fminf(fmaxf(x1, -4.0f), 4.0f));
-  const uint64_t t = mul2(xc, xc);
-  uint64_t p = fma2(splat2(2.27813761e-08f), t, splat2(-1.59859863e-06f));
-  p = fma2(p, t, splat2(4.79554370e-05f));
-  p = fma2(p, t, splat2(-8.14014580e-04f));
-  p = fma2(p, t, splat2(8.77238349e-03f));
-  p = fma2(p, t, splat2(-6.45730991e-02f));
-  p = fma2(p, t, splat2(3.97883340e-01f));
-  return mul2(x, fma2(xc, p, splat2(0.5f)));
-}
 // swish(x) = x * sigmoid(x) = x * (0.5 * tanh(x / 2) + 0.5): ONE MUFU op per element (tanh.approx, rel. error 2^-11)
 // instead of ex2 + rcp -- the swish epilogues of the MBConv GEMMs / depthwise kernels are MUFU-throughput bound
 // (16 MUFU lanes per SM per clock).
@@ -185,7 +147,8 @@ __device__ __forceinline__ uint64_t swish_fast2(uint64_t x) {
 // by the odd quintic x (a + b x^2 + c x^4) on |x| <= 6 (minimax for the error of x Phi: 2.5e-5 -- the usual two-term
 // "tanh GELU" is 4.7e-4 off the erf form), the argument is clamped because the quintic turns over beyond |x| ~ 11.
 // With tanh.approx (rel. error 2^-11) the result is within 2.5e-4 |x| of the exact erf GELU.  6 FMA-pipe operations
-// + 2 MUFU per PAIR: MUFU bound at 16 elements/clk/SM, against 12.5 for the pure-FMA polynomial gelu_poly2.
+// + 2 MUFU per PAIR: MUFU bound at 16 elements/clk/SM, against 12.5 measured for a pure-FMA degree-6 erf polynomial
+// (9 FMA-pipe operations per element) and 8 for the erfc formula with ex2 + rcp (4 MUFU per pair).
 __device__ __forceinline__ uint64_t gelu_tanh2(uint64_t x) {
   float x0, x1;
   unpack2(x, x0, x1);

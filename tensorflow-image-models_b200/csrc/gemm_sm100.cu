@@ -309,7 +309,11 @@ int launch_conv(const void* x, const void* W, int ldw, const void* residual, voi
     }
   }
   auto kernel = gemm_bf16_tcgen05_kernel<BLOCK_N, OutT>;
-  TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
   const int tiles = (p.M / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kernel<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, tc, p);
