@@ -319,6 +319,54 @@ __global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out,
   }
 }
 
+// RGB 7x7 / stride-2 stem (ResNet conv1, tfimm/architectures/resnet.py:486-494): an im2col row is seven runs of
+// 21 CONTIGUOUS input values, out[m][ky*21 + j] = x[b][2 oy - pad_t + ky][(2 ox - pad_l) * 3 + j].  The generic
+// kernel gathers them as 4-byte global loads per element (1.0 ms for 256 x 224 x 224 x 3: 7x its HBM time); here a
+// CTA stages the 7 input rows of 32 output pixels in shared memory with coalesced loads (converted to bf16 once)
+// and every thread assembles 16-byte output chunks from there.
+template <typename InT>
+__global__ void __launch_bounds__(256)
+im2col_stem7_kernel(const InT* __restrict__ x, __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo,
+                    int pad_t, int pad_l, int Kpad) {
+  constexpr int TW = 32;                  // output pixels per CTA
+  constexpr int ROW = ((TW - 1) * 2 + 7) * 3;  // 207 input values per tap row
+  __shared__ __nv_bfloat16 tile[7][ROW + 1];
+  const int segs = (Wo + TW - 1) / TW;
+  int t = blockIdx.x;
+  const int seg = t % segs; t /= segs;
+  const int oy = t % Ho;
+  const int b = t / Ho;
+  const int ox0 = seg * TW;
+  const int e0 = (ox0 * 2 - pad_l) * 3;   // first element (within an image row of W*3 values) of the tile
+  const int iy0 = oy * 2 - pad_t;
+  for (int idx = threadIdx.x; idx < 7 * ROW; idx += 256) {
+    const int r = idx / ROW, e = idx - r * ROW;
+    const int iy = iy0 + r, ge = e0 + e;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ge >= 0 && ge < W * 3) v = ld_as_float(x + ((long)b * H + iy) * W * 3 + ge);
+    tile[r][e] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int chunks = Kpad >> 3;
+  for (int task = threadIdx.x; task < TW * chunks; task += 256) {
+    const int p = task / chunks, ch = task - p * chunks;
+    if (ox0 + p >= Wo) continue;
+    uint32_t packed[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      uint16_t h[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = ch * 8 + j + u;
+        h[u] = k < 147 ? __bfloat16_as_ushort(tile[k / 21][p * 6 + k % 21]) : (uint16_t)0;
+      }
+      packed[j / 2] = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+    }
+    const long m = ((long)b * Ho + oy) * Wo + ox0 + p;
+    *reinterpret_cast<uint4*>(out + m * Kpad + ch * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // squeeze-excite gate: pooled sums -> 1x1 conv (bias) -> act -> 1x1 conv (bias) -> gate act
 // ----------------------------------------------------------------------------------------------
@@ -450,7 +498,22 @@ int im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, 
 #define TFIMM_I2C_STEM(IN, OUT, KS_T)                                                                         \
   im2col_kernel<IN, OUT, KS_T, 3><<<grid, 256, 0, stream>>>(reinterpret_cast<const IN*>(x), reinterpret_cast<OUT*>(out), \
                                                            B, H, W, C, groups, Ho, Wo, ks, stride, pad_t, pad_l, Kpad)
-  if (C == 3 && groups == 1 && (ks == 7 || ks == 3) && out_dtype == kBF16 && (in_dtype == kF32 || in_dtype == kBF16)) {
+  static const bool stem_tiled = [] {
+    const char* e = getenv("TFIMM_B200_STEM");  // "generic": per-element gather kernel (A/B)
+    return e == nullptr || e[0] != 'g';
+  }();
+  if (stem_tiled && C == 3 && groups == 1 && ks == 7 && stride == 2 && out_dtype == kBF16 && Kpad >= 147 &&
+      (in_dtype == kF32 || in_dtype == kBF16)) {
+    const long ctas = (long)B * Ho * ((Wo + 31) / 32);
+    if (in_dtype == kF32)
+      im2col_stem7_kernel<<<(unsigned)ctas, 256, 0, stream>>>(reinterpret_cast<const float*>(x),
+                                                           reinterpret_cast<__nv_bfloat16*>(out), H, W, Ho, Wo, pad_t,
+                                                           pad_l, Kpad);
+    else
+      im2col_stem7_kernel<<<(unsigned)ctas, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                           reinterpret_cast<__nv_bfloat16*>(out), H, W, Ho, Wo, pad_t,
+                                                           pad_l, Kpad);
+  } else if (C == 3 && groups == 1 && (ks == 7 || ks == 3) && out_dtype == kBF16 && (in_dtype == kF32 || in_dtype == kBF16)) {
     if (in_dtype == kF32) { if (ks == 7) TFIMM_I2C_STEM(float, __nv_bfloat16, 7); else TFIMM_I2C_STEM(float, __nv_bfloat16, 3); }
     else { if (ks == 7) TFIMM_I2C_STEM(__nv_bfloat16, __nv_bfloat16, 7); else TFIMM_I2C_STEM(__nv_bfloat16, __nv_bfloat16, 3); }
   } else if (in_dtype == kF32 && out_dtype == kBF16) TFIMM_I2C(float, __nv_bfloat16);

@@ -512,6 +512,24 @@ def test_im2col_gemm_equals_conv(ks, stride, padding, C):
     assert (out - ref).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W", [(2, 37, 45), (1, 224, 224), (3, 64, 33)])
+def test_im2col_rgb_stem_bf16_is_exact(B, H, W, in_dtype):
+    """7x7 / stride-2 / pad-3 im2col of an RGB image into bf16 (the tiled shared-memory stem kernel): a pure gather,
+    so it must equal torch's unfold of the bf16-rounded input bit for bit, in TF's (ky, kx, c) column order."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(H + W)
+    x = torch.randn(B, H, W, 3, device="cuda", generator=g).to(in_dtype)
+    cols, Ho, Wo = ops.im2col(x, 7, 2, 3, torch.bfloat16)
+    torch.cuda.synchronize()
+    assert (Ho, Wo) == ((H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1) and cols.shape == (B * Ho * Wo, 152)
+    xb = x.to(torch.bfloat16).float().permute(0, 3, 1, 2)                       # (B, 3, H, W)
+    ref = torch.nn.functional.unfold(xb, 7, padding=3, stride=2)                  # (B, 3*49, L), rows ordered (c, ky, kx)
+    ref = ref.view(B, 3, 49, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 147)  # -> (m, (ky, kx), c)
+    assert torch.equal(cols[:, :147].float(), ref)
+    assert (cols[:, 147:] == 0).all()
+
+
 def test_se_gate_scale_and_eca():
     ops = _ops()
     B, H, W, C, rd = 3, 5, 7, 48, 6
