@@ -101,7 +101,8 @@ def test_create_model_errors_and_overrides(caplog):
 
 def test_every_registration_constructs():
     """All 186 registrations build their variables (meta device: shapes only) -- none is left unimplemented."""
-    names = tfimm.list_models()
+    names = [n for fam in ("vit", "swin", "convnext", "efficientnet", "resnet")
+             for n in json.loads((ZOO / f"{fam}.json").read_text())]  # (other tests register scratch models)
     assert len(names) == 186
     for name in names:
         m = tfimm.create_model(name, device="meta")
