@@ -251,5 +251,13 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name, argtypes in lib.SIGNATURES.items():
         m = re.search(name + r"\s*\(([^;]*?)\)\s*;", header, re.S)
         assert m, name
-        nparams = len([p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"])
-        assert nparams == len(argtypes), (name, nparams, len(argtypes))
+        params = [p.strip() for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        # ... and so does the kind of every parameter (pointer / int / long / float): a float passed as int, or a
+        # 64-bit stride passed as int, would be silent garbage through ctypes
+        import ctypes
+
+        for p, ct in zip(params, argtypes):
+            want = ctypes.c_void_p if "*" in p else ctypes.c_float if p.startswith("float") else \
+                ctypes.c_long if p.startswith("long") else ctypes.c_int
+            assert ct is want, (name, p, ct)
