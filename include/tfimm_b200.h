@@ -63,24 +63,6 @@ int tfimm_b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, const f
                          const float* gamma, const void* residual, int ldr, void* C, int ldc, int M, int N,
                          int K, int act, int act_after_residual, int out_dtype, int force_block_n, void* stream);
 
-/* LayerNorm folded into the dense layer that follows it (tf.keras.layers.LayerNormalization -> Dense at
- * tfimm/architectures/vit.py:240-262, swin.py:262-300, convnext.py:197-226): same contraction as
- * tfimm_b200_gemm_bf16 with two optional extras.
- *   consumer side (ln_stats != NULL): A holds the RAW rows x in bf16, W = bf16(gamma_ln * W), bias already
- *     contains W beta_ln, ln_colsum[n] = sum_k W[n][k]; per-row mean/rstd are rebuilt from ln_parts partial
- *     (sum, sum of squares) pairs per row, ln_stats[M][ln_parts][2], and applied in the epilogue:
- *     LN(x) W^T = rstd * (x W^T - mean * colsum).  The normalised dimension is K.
- *   producer side (emit_stats != NULL): besides C, writes this GEMM's per-row partial statistics
- *     emit_stats[M][emit_parts][2] (emit_parts must equal tfimm_b200_gemm_stat_parts(M, N, force_block_n)) and,
- *     if emit_bf16 != NULL (fp32 C only), a bf16 copy of C, the A operand of the next folded GEMM.
- * This removes the standalone LayerNorm pass over the fp32 residual stream. */
-int tfimm_b200_gemm_bf16_ln(const void* A, int lda, const void* W, int ldw, const float* bias,
-                            const float* gamma, const void* residual, int ldr, void* C, int ldc, int M, int N,
-                            int K, int act, int act_after_residual, int out_dtype, int force_block_n,
-                            const float* ln_stats, int ln_parts, const float* ln_colsum, float ln_eps,
-                            void* emit_bf16, int ld_emit, float* emit_stats, int emit_parts, void* stream);
-int tfimm_b200_gemm_stat_parts(int M, int N, int force_block_n);
-
 /* Dense k x k convolution (+ folded-BN bias, activation, optional residual, act(x + shortcut)) as an IMPLICIT GEMM
  * on the tcgen05 tensor cores: tf.keras.layers.ZeroPadding2D(pad) + Conv2D(k, strides) (+ BatchNormalization, act)
  * at tfimm/architectures/resnet.py:129-150 (BasicBlock 3x3), 230-238 (Bottleneck conv2), 486-512 (deep stems).
@@ -91,10 +73,6 @@ int tfimm_b200_gemm_stat_parts(int M, int N, int force_block_n);
 int tfimm_b200_conv_bf16(const void* x, const void* W, int ldw, const float* bias, const void* residual, void* out,
                          int B, int H, int Wd, int C, int N, int ks, int stride, int pad, int act,
                          int act_after_residual, int out_dtype, void* stream);
-/* bf16 copy + one (sum, sum of squares) partial per row of an fp32 [rows][C] matrix: entry point of a
- * LayerNorm-folded stream (after the token assembly / patch embedding, which are not GEMM epilogues). */
-int tfimm_b200_row_stats_cast(const float* x, long in_stride, void* out_bf16, long out_stride, float* stats,
-                              long rows, int C, void* stream);
 
 /* Same contract in fp32 on CUDA cores (precision="fp32" parity mode). */
 int tfimm_b200_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
@@ -167,15 +145,6 @@ int tfimm_b200_assemble_tokens(const void* patches, int patch_dtype, const float
 int tfimm_b200_dwconv_ln(const void* x, int in_dtype, const float* wgt, const float* bias, const float* gamma,
                          const float* beta, void* out, int out_dtype, int B, int H, int W, int C, int ks,
                          float eps, void* stream);
-
-/* ConvNeXt block head with the LayerNorm folded into the following Dense (tfimm/architectures/convnext.py:219-224):
- * ZeroPadding2D(3) + DepthwiseConv2D(7, bias) only.  x: fp32 NHWC (the residual stream); out_bf16: the RAW convolution
- * result, the A operand of tfimm_b200_gemm_bf16_ln; stats: [B*H*W][parts][2] per-pixel partial (sum, sum of squares)
- * of the fp32 results, one pair per 64- (or 32-) channel slab, parts = tfimm_b200_dwconv7_stats_parts(C).
- * No thread-block clusters, no LayerNorm passes: one 4-D TMA halo box per tile, FFMA2 taps, register stores. */
-int tfimm_b200_dwconv7_stats(const float* x, const float* wgt, const float* bias, void* out_bf16, float* stats, int B,
-                             int H, int W, int C, void* stream);
-int tfimm_b200_dwconv7_stats_parts(int C);
 
 /* DepthwiseConv2D(k in {3,5,7}, stride in {1,2}) with explicit top/left zero padding (covers TF "same"
  * and PadDepthwiseConv2D "symmetric", tfimm/layers/conv.py:91-148) + per-channel bias (folded BatchNorm)

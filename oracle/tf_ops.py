@@ -175,13 +175,29 @@ def _keys_cubic(x):
 
 
 def resize_bicubic(images, size):
-    """tf.image.resize(method="bicubic"): Keys cubic A=-0.5, half-pixel centres, out-of-image taps
-    dropped and weights renormalised (scale_and_translate_op.cc)."""
+    """tf.image.resize(method="bicubic", antialias=False) = ResizeBicubic(half_pixel_centers=True)
+    (resize_bicubic_op.cc): Keys cubic A=-0.5 tabulated at 1024 steps, float32 source coordinate, out-of-image taps
+    get weight 0 and the rest are renormalised."""
+    import numpy as np
+
     def matrix(n_in, n_out):
-        centers = (torch.arange(n_out, dtype=torch.float64) + 0.5) * (n_in / n_out)
-        src = torch.arange(n_in, dtype=torch.float64) + 0.5
-        w = _keys_cubic(src[None, :] - centers[:, None])
-        return (w / w.sum(dim=1, keepdim=True)).to(images.dtype)
+        table, a = 1024, -0.5
+        scale = np.float32(n_in) / np.float32(n_out)
+        w = np.zeros((n_out, n_in), dtype=np.float32)
+        for o in range(n_out):
+            src = np.float32(np.float32(o + 0.5) * scale) - np.float32(0.5)
+            base = int(np.floor(src))
+            off = int(np.rint(np.float32(src - np.float32(base)) * np.float32(table)))
+            taps = []
+            for k, x in ((-1, off / table + 1.0), (0, off / table), (1, (table - off) / table),
+                         (2, (table - off) / table + 1.0)):
+                val = ((a + 2) * x - (a + 3)) * x * x + 1 if x <= 1.0 else ((a * x - 5 * a) * x + 8 * a) * x - 4 * a
+                if 0 <= base + k < n_in:
+                    taps.append((base + k, np.float32(val)))
+            tot = np.float32(sum(t[1] for t in taps))
+            for idx, val in taps:
+                w[o, idx] += np.float32(val / tot)
+        return torch.from_numpy(w).to(images.dtype)
 
     out = torch.einsum("oh,bhwc->bowc", matrix(images.shape[1], size[0]), images)
     return torch.einsum("pw,bowc->bopc", matrix(images.shape[2], size[1]), out)

@@ -40,15 +40,10 @@ int sm_count() {
 
 // implemented in the other translation units
 int gemm_bf16_dispatch(const void*, int, const void*, int, const float*, const float*, const void*, int, void*,
-                       int, int, int, int, int, int, int, int, const float*, int, const float*, float, void*, int,
-                       float*, int, cudaStream_t);
-int gemm_bf16_stat_parts(int, int, int);
-int dwconv7_stats(const void*, const float*, const float*, void*, float*, int, int, int, int, cudaStream_t);
-int dwconv7_stats_parts(int);
+                       int, int, int, int, int, int, int, int, cudaStream_t);
 int attention_cls_bf16(const void*, void*, int, int, int, int, int, float, cudaStream_t);
 int conv_bf16_dispatch(const void*, const void*, int, const float*, const void*, void*, int, int, int, int, int, int,
                        int, int, int, int, int, cudaStream_t);
-int row_stats_cast(const float*, long, void*, long, float*, long, int, cudaStream_t);
 int gemm_f32(const float*, int, const float*, int, const float*, const float*, const float*, int, float*, int,
              int, int, int, int, int, cudaStream_t);
 int layernorm_rows(const void*, int, long, const float*, const float*, void*, int, long, long, int, float,
@@ -100,18 +95,7 @@ int tfimm_b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, const f
                          const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act,
                          int act_after_residual, int out_dtype, int force_block_n, void* stream) {
   return tfimm::gemm_bf16_dispatch(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act,
-                                   act_after_residual, out_dtype, force_block_n, nullptr, 0, nullptr, 0.f, nullptr, 0,
-                                   nullptr, 0, S(stream));
-}
-
-int tfimm_b200_gemm_bf16_ln(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
-                            const void* residual, int ldr, void* C, int ldc, int M, int N, int K, int act,
-                            int act_after_residual, int out_dtype, int force_block_n, const float* ln_stats,
-                            int ln_parts, const float* ln_colsum, float ln_eps, void* emit_bf16, int ld_emit,
-                            float* emit_stats, int emit_parts, void* stream) {
-  return tfimm::gemm_bf16_dispatch(A, lda, W, ldw, bias, gamma, residual, ldr, C, ldc, M, N, K, act,
-                                   act_after_residual, out_dtype, force_block_n, ln_stats, ln_parts, ln_colsum,
-                                   ln_eps, emit_bf16, ld_emit, emit_stats, emit_parts, S(stream));
+                                   act_after_residual, out_dtype, force_block_n, S(stream));
 }
 
 int tfimm_b200_conv_bf16(const void* x, const void* W, int ldw, const float* bias, const void* residual, void* out,
@@ -124,22 +108,6 @@ int tfimm_b200_conv_bf16(const void* x, const void* W, int ldw, const float* bia
 int tfimm_b200_attention_cls_bf16(const void* qkv, void* out, int B, int N, int H, int head_dim, int nq, float scale,
                                   void* stream) {
   return tfimm::attention_cls_bf16(qkv, out, B, N, H, head_dim, nq, scale, S(stream));
-}
-
-int tfimm_b200_dwconv7_stats(const float* x, const float* wgt, const float* bias, void* out_bf16, float* stats, int B,
-                             int H, int W, int C, void* stream) {
-  return tfimm::dwconv7_stats(x, wgt, bias, out_bf16, stats, B, H, W, C, S(stream));
-}
-
-int tfimm_b200_dwconv7_stats_parts(int C) { return tfimm::dwconv7_stats_parts(C); }
-
-int tfimm_b200_gemm_stat_parts(int M, int N, int force_block_n) {
-  return tfimm::gemm_bf16_stat_parts(M, N, force_block_n);
-}
-
-int tfimm_b200_row_stats_cast(const float* x, long in_stride, void* out_bf16, long out_stride, float* stats,
-                              long rows, int C, void* stream) {
-  return tfimm::row_stats_cast(x, in_stride, out_bf16, out_stride, stats, rows, C, S(stream));
 }
 
 int tfimm_b200_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias, const float* gamma,

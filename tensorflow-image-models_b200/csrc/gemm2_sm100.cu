@@ -42,8 +42,7 @@ struct PairCfg {
   static constexpr int kNumEpiWarps = 4 * kEpiGroups;
   static constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
   static constexpr int kSlabBytes = 32 * kCH * (int)sizeof(OutT);                     // 2 KB (bf16) / 4 KB (fp32)
-  static constexpr int kCopySlabBytes = sizeof(OutT) == 4 ? kEpiCopySlabBytes : 0;    // bf16 copy (emit mode)
-  static constexpr int kSlabTotal = kNumEpiWarps * (kSlabBytes + kCopySlabBytes);
+  static constexpr int kSlabTotal = kNumEpiWarps * kSlabBytes;
   static constexpr int kStages = 5;
   static constexpr int kNumBarriers = 2 * kStages + 2 * kAccStages + kNumEpiWarps;
   static constexpr int kSmemBytes = kStages * kStageBytes + kSlabTotal + kNumBarriers * 8 + 16 + 1024 /*align*/;
@@ -55,8 +54,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<OutT>::kNumT
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                               const __grid_constant__ CUtensorMap tmap_b,
                               const __grid_constant__ CUtensorMap tmap_c,
-                              const __grid_constant__ CUtensorMap tmap_r,
-                              const __grid_constant__ CUtensorMap tmap_c2, const GemmParams p) {
+                              const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
   using Cfg = PairCfg<OutT>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kNumEpiWarps = Cfg::kNumEpiWarps;
@@ -175,8 +173,6 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int grp = ew >> 2;             // which share of the column chunks this warp takes
     const uint32_t slab = smem_slabs + (uint32_t)ew * Cfg::kSlabBytes;
     uint8_t* my_row = smem_gen + (slab - smem_base) + lane * (Cfg::kSlabBytes / 32);
-    const uint32_t copy_slab = smem_slabs + kNumEpiWarps * Cfg::kSlabBytes + (uint32_t)ew * Cfg::kCopySlabBytes;
-    uint8_t* copy_row = smem_gen + (copy_slab - smem_base) + lane * 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t cc = 0;  // chunks processed by this warp (residual barrier parity)
@@ -195,19 +191,14 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (lane == 0) mbar_arrive_cluster(tempty_leader);
       };
       if (grp >= nvalid) release_acc();  // nothing to read for this warp in this tile
-      float ln_rstd = 1.f, ln_nmr = 0.f, stat_s = 0.f, stat_q = 0.f;
-      if (p.ln_stats != nullptr) ln_row_coeffs(p, row0 + lane, ln_rstd, ln_nmr);
 #pragma unroll 1
       for (int c = grp; c < nvalid; c += kEpiGroups) {
         const int n0 = n_blk * kBlockN + c * kCH;
         const bool last = c + kEpiGroups >= nvalid;
         epilogue_chunk<OutT, kCH>(p, t_acc + (uint32_t)(c * kCH), n0, row0, slab, my_row, lane, res_bar(ew), cc & 1u,
-                                  &tmap_c, &tmap_r, &tmap_c2, copy_slab, copy_row, ln_rstd, ln_nmr, stat_s, stat_q,
-                                  /*ct=*/nullptr, [&]() { if (last) release_acc(); });
+                                  &tmap_c, &tmap_r, /*ct=*/nullptr, [&]() { if (last) release_acc(); });
         ++cc;
       }
-      if (p.emit_stats != nullptr)
-        emit_row_stats(p, row0 + lane, kEpiGroups * n_blk + grp, kEpiGroups * num_n_tiles, stat_s, stat_q);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -240,10 +231,6 @@ int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const void*
   } else {
     tr = tc;
   }
-  CUtensorMap tc2 = tc;
-  if (p.emit_bf16 != nullptr) {
-    if ((st = make_tmap_2d(&tc2, p.emit_bf16, kBF16, M, N, p.ld_emit, 32, 32, "bf16 copy", 64)) != kOk) return st;
-  }
   auto kernel = gemm_bf16_tcgen05_pair_kernel<OutT>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -253,15 +240,12 @@ int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const void*
   const int tiles = ((M + kPairM - 1) / kPairM) * ((N + kBlockN - 1) / kBlockN);
   const int max_pairs = sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  kernel<<<2 * pairs, Cfg::kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, tc2, p);
+  kernel<<<2 * pairs, Cfg::kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, p);
   TFIMM_LAUNCH_OK("gemm_bf16_tcgen05_pair_kernel");
   return kOk;
 }
 
 }  // namespace
-
-// Partial statistics per row a statistics-emitting launch of this kernel writes per 256-column tile.
-int gemm_bf16_pair_stat_groups(int out_dtype) { return out_dtype == kBF16 ? 4 : 2; }
 
 int gemm_bf16_pair(const void* A, int lda, const void* W, int ldw, const void* residual, int ldr, void* C, int ldc,
                    const GemmParams& p, int out_dtype, cudaStream_t stream) {

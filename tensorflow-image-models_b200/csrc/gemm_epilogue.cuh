@@ -16,20 +16,6 @@ struct GemmParams {
   int act;
   int has_res;
   int act_post;  // 1: activation applied after the residual add (ResNet: act(x + shortcut))
-  // LayerNorm folded into this GEMM: A holds the RAW rows x (bf16), W has the LayerNorm gamma folded in and
-  // bias the beta term; with colsum[n] = sum_k W[n][k] the normalised product is recovered per row r as
-  //     LN(x) W^T = rstd_r * (x W^T - mean_r * colsum)
-  // mean/rstd come from per-row partial (sum, sum of squares) statistics written by the producer of x.
-  const float* ln_stats;   // [M][ln_parts][2], or null (no folding)
-  const float* ln_colsum;  // [N]
-  int ln_parts;
-  float ln_inv_dim;        // 1 / (number of normalised features)
-  float ln_eps;
-  // Producer side of the same scheme: besides C, emit a bf16 copy of the result rows (the A operand of the
-  // next, LayerNorm-folded GEMM) and this tile's per-row partial statistics of the fp32 results.
-  __nv_bfloat16* emit_bf16;  // [M][ld_emit], or null (C itself is bf16 / no copy wanted)
-  int ld_emit;
-  float* emit_stats;         // [M][2 * ceil(N / tile N)][2], or null
   // Implicit convolution (gemm_sm100.cu): the A operand is not a matrix but the NHWC input itself.  A tile's 128
   // rows are a patch of cv_pb images x cv_ph rows x cv_pw columns of OUTPUT pixels; k-block kb is tap
   // (ky, kx) = kb / (C/64) and 64 input channels, fetched as ONE 4-D TMA box whose out-of-bounds elements are
@@ -45,56 +31,7 @@ struct ConvTile {
   int x, y, b;  // output-pixel coordinates of a warp's first row
 };
 
-// mean / rstd of row `row` from the partial statistics; returned as (rstd, -mean * rstd).
-__device__ __forceinline__ void ln_row_coeffs(const GemmParams& p, int row, float& rstd, float& nmr) {
-  float s = 0.f, q = 0.f;
-  if (row < p.M) {
-    const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)row * p.ln_parts;
-    for (int i = 0; i < p.ln_parts; ++i) {
-      const float2 v = __ldg(st + i);
-      s += v.x;
-      q += v.y;
-    }
-  }
-  const float mean = s * p.ln_inv_dim;
-  const float var = fmaxf(q * p.ln_inv_dim - mean * mean, 0.f);
-  rstd = rsqrtf(var + p.ln_eps);
-  nmr = -mean * rstd;
-}
-
-// v[j] = rstd * v[j] + (nmr * colsum[n0 + j] + bias[n0 + j])      (two packed FMAs per pair, bias included)
-template <int CH>
-__device__ __forceinline__ void apply_ln_fold(uint64_t (&v)[CH / 2], const float* __restrict__ cs,
-                                              const float* __restrict__ bias, int n0, int N, float rstd, float nmr) {
-  const uint64_t r2 = splat2(rstd), m2 = splat2(nmr);
-  if (n0 + CH <= N) {
-#pragma unroll
-    for (int j = 0; j < CH; j += 4) {
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + n0 + j));
-      const float4 b4 = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + n0 + j))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-      v[j / 2] = fma2(v[j / 2], r2, fma2(m2, pack2(c4.x, c4.y), pack2(b4.x, b4.y)));
-      v[j / 2 + 1] = fma2(v[j / 2 + 1], r2, fma2(m2, pack2(c4.z, c4.w), pack2(b4.z, b4.w)));
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < CH; j += 2) {
-      const bool ok0 = n0 + j < N, ok1 = n0 + j + 1 < N;
-      const float c0 = ok0 ? __ldg(cs + n0 + j) : 0.f, c1 = ok1 ? __ldg(cs + n0 + j + 1) : 0.f;
-      const float b0 = (ok0 && bias != nullptr) ? __ldg(bias + n0 + j) : 0.f;
-      const float b1 = (ok1 && bias != nullptr) ? __ldg(bias + n0 + j + 1) : 0.f;
-      v[j / 2] = fma2(v[j / 2], r2, fma2(m2, pack2(c0, c1), pack2(b0, b1)));
-    }
-  }
-}
-
-// End of a tile: this warp's partial statistics of its rows (part = 2 * n_blk + column-chunk group).
-__device__ __forceinline__ void emit_row_stats(const GemmParams& p, int row, int part, int parts, float s, float q) {
-  if (row < p.M) reinterpret_cast<float2*>(p.emit_stats)[(size_t)row * parts + part] = make_float2(s, q);
-}
-
 constexpr int kEpiSlabBytes = 32 * 128;     // 32 rows x 128 B, one per epilogue warp
-constexpr int kEpiCopySlabBytes = 32 * 64;  // 32 rows x 32 bf16: the bf16 copy of an fp32 chunk (emit mode)
 
 // v[j] (+ or *)= vec[n0 + j] on packed pairs; full chunks use 16-byte loads.
 template <int CH, bool kMul>
@@ -159,9 +96,7 @@ template <typename OutT, int CHW = 128 / (int)sizeof(OutT), typename AfterLoad>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_addr, int n0, int row0,
                                                uint32_t slab, uint8_t* my_row, int lane, uint32_t res_bar,
                                                uint32_t res_parity, const CUtensorMap* tmap_c,
-                                               const CUtensorMap* tmap_r, const CUtensorMap* tmap_c2,
-                                               uint32_t copy_slab, uint8_t* copy_row, float ln_rstd, float ln_nmr,
-                                               float& stat_s, float& stat_q, const ConvTile* ct,
+                                               const CUtensorMap* tmap_r, const ConvTile* ct,
                                                AfterLoad after_load) {
   constexpr int CH = CHW;
   constexpr int RB = CH * (int)sizeof(OutT);  // bytes per slab row: 128 or 64
@@ -192,8 +127,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_a
     }
   }
   after_load();
-  if (p.ln_stats != nullptr) apply_ln_fold<CH>(v, p.ln_colsum, p.bias, n0, p.N, ln_rstd, ln_nmr);
-  else if (p.bias != nullptr) apply_vec<CH, false>(v, p.bias, n0, p.N);
+  if (p.bias != nullptr) apply_vec<CH, false>(v, p.bias, n0, p.N);
   if (!p.act_post) apply_act_pairs(v, p.act);
   if (p.gamma != nullptr) apply_vec<CH, true>(v, p.gamma, n0, p.N);
   if (p.has_res) {
@@ -215,37 +149,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_a
     }
   }
   if (p.act_post) apply_act_pairs(v, p.act);
-  if (p.emit_stats != nullptr) {
-    // partial LayerNorm statistics of the fp32 results (dispatch guarantees N % CH == 0 in this mode)
-    uint64_t s2 = pack2(stat_s, 0.f), q2 = pack2(stat_q, 0.f);
-#pragma unroll
-    for (int j = 0; j < CH / 2; ++j) {
-      s2 = add2(s2, v[j]);
-      q2 = fma2(v[j], v[j], q2);
-    }
-    float a, b;
-    unpack2(s2, a, b);
-    stat_s = a + b;
-    unpack2(q2, a, b);
-    stat_q = a + b;
-    if constexpr (sizeof(OutT) == 4) {
-      if (p.emit_bf16 != nullptr) {
-        // bf16 copy of the 32 x 32 chunk: 64-byte rows in a second, 64B-swizzled slab -> its own TMA store
-        // (16-byte unit j of row r lives at j ^ ((r >> 1) & 3): conflict-free for the 32 row-owning lanes)
-        const int sw2 = (lane >> 1) & 3;
-#pragma unroll
-        for (int j = 0; j < CH / 8; ++j) {
-          float a0, a1, a2, a3, a4, a5, a6, a7;
-          unpack2(v[4 * j + 0], a0, a1);
-          unpack2(v[4 * j + 1], a2, a3);
-          unpack2(v[4 * j + 2], a4, a5);
-          unpack2(v[4 * j + 3], a6, a7);
-          *reinterpret_cast<uint4*>(copy_row + ((j ^ sw2) << 4)) =
-              make_uint4(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3), pack_bf16x2(a4, a5), pack_bf16x2(a6, a7));
-        }
-      }
-    }
-  }
 #pragma unroll
   for (int j = 0; j < UNITS; ++j) {
     uint4 u;
@@ -275,9 +178,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_a
   if (lane == 0) {
     if (ct == nullptr) tma_store_2d(tmap_c, slab, n0, row0);
     else tma_store_4d(tmap_c, slab, n0, ct->x, ct->y, ct->b);
-    if constexpr (sizeof(OutT) == 4) {
-      if (p.emit_bf16 != nullptr) tma_store_2d(tmap_c2, copy_slab, n0, row0);
-    }
     tma_store_commit();
   }
 }

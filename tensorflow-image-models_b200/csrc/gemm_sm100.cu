@@ -41,10 +41,7 @@ struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 5 : 7);
-  // bf16-copy slabs (statistics/copy-emitting epilogue) only where shared memory allows: not for BLOCK_N = 256,
-  // whose emitting GEMMs go to the CTA-pair kernel or to BLOCK_N = 128 (see gemm_bf16_dispatch)
-  static constexpr bool kHasCopySlab = BLOCK_N != 256;
-  static constexpr int kSlabTotal = kNumEpiWarps * (kSlabBytes + (kHasCopySlab ? kEpiCopySlabBytes : 0));
+  static constexpr int kSlabTotal = kNumEpiWarps * kSlabBytes;
   static constexpr int kNumBarriers = 2 * kStages + 2 * kAccStages + kNumEpiWarps;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kSlabTotal + kNumBarriers * 8 + 16 + 1024 /*alignment slack*/;
@@ -56,8 +53,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c,
-                         const __grid_constant__ CUtensorMap tmap_r,
-                         const __grid_constant__ CUtensorMap tmap_c2, const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
   constexpr int CH = 128 / (int)sizeof(OutT);  // output columns per 128-byte slab row
@@ -176,8 +172,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int grp = ew >> 2;             // which half of the column chunks this warp takes
     const uint32_t slab = smem_slabs + (uint32_t)ew * kSlabBytes;
     uint8_t* my_row = smem_gen + (slab - smem_base) + lane * 128;
-    const uint32_t copy_slab = smem_slabs + kNumEpiWarps * kSlabBytes + (uint32_t)ew * kEpiCopySlabBytes;
-    uint8_t* copy_row = smem_gen + (copy_slab - smem_base) + lane * 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t cc = 0;  // chunks processed by this warp (residual barrier parity)
@@ -205,14 +199,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-      float ln_rstd = 1.f, ln_nmr = 0.f, stat_s = 0.f, stat_q = 0.f;
-      if (p.ln_stats != nullptr) ln_row_coeffs(p, row0 + lane, ln_rstd, ln_nmr);
 #pragma unroll 1
       for (int c = grp; c < nvalid; c += 2) {
         const int n0 = n_blk * BLOCK_N + c * CH;
         const bool last = c + 2 >= nvalid;
         epilogue_chunk<OutT>(p, t_acc + (uint32_t)(c * CH), n0, row0, slab, my_row, lane, res_bar(ew), cc & 1u,
-                             &tmap_c, &tmap_r, &tmap_c2, copy_slab, copy_row, ln_rstd, ln_nmr, stat_s, stat_q, ct, [&]() {
+                             &tmap_c, &tmap_r, ct, [&]() {
                                if (last) {
                                  // all TMEM reads of this accumulator stage by this warp are done
                                  tcgen05_fence_before();
@@ -222,7 +214,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                              });
         ++cc;
       }
-      if (p.emit_stats != nullptr) emit_row_stats(p, row0 + lane, 2 * n_blk + grp, 2 * num_n_tiles, stat_s, stat_q);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -254,14 +245,6 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, const void* resi
   } else {
     tr = tc;
   }
-  CUtensorMap tc2 = tc;
-  if (p.emit_bf16 != nullptr) {
-    if (!Cfg::kHasCopySlab) {
-      set_last_error("gemm: the bf16 copy is not available with the one-CTA BLOCK_N = 256 tiling");
-      return kInvalidArgument;
-    }
-    if ((st = make_tmap_2d(&tc2, p.emit_bf16, kBF16, M, N, p.ld_emit, 32, 32, "bf16 copy", 64)) != kOk) return st;
-  }
   auto kernel = gemm_bf16_tcgen05_kernel<BLOCK_N, OutT>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -270,7 +253,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, const void* resi
   }
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kernel<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, tc2, p);
+  kernel<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, p);
   TFIMM_LAUNCH_OK("gemm_bf16_tcgen05_kernel");
   return kOk;
 }
@@ -316,7 +299,7 @@ int launch_conv(const void* x, const void* W, int ldw, const void* residual, voi
   }
   const int tiles = (p.M / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kernel<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, tc, p);
+  kernel<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, p);
   TFIMM_LAUNCH_OK("gemm_bf16_tcgen05_kernel (implicit convolution)");
   return kOk;
 }
@@ -359,44 +342,20 @@ bool prefer_pair(int M, int N) {
 
 }  // namespace
 
-// ln / emit: see GemmParams.  emit_parts_out (optional) receives the number of partial statistics per row
-// that the chosen tiling writes (2 x number of N tiles).
 int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const float* bias,
                        const float* gamma, const void* residual, int ldr, void* C, int ldc, int M,
-                       int N, int K, int act, int act_post, int out_dtype, int force_block_n,
-                       const float* ln_stats, int ln_parts, const float* ln_colsum, float ln_eps, void* emit_bf16,
-                       int ld_emit, float* emit_stats, int emit_parts, cudaStream_t stream) {
+                       int N, int K, int act, int act_post, int out_dtype, int force_block_n, cudaStream_t stream) {
   TFIMM_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: M, N, K must be positive (got %d %d %d)", M, N, K);
   TFIMM_CHECK_ARG(out_dtype == kBF16 || out_dtype == kF32, "gemm: out_dtype must be bf16 or f32");
   TFIMM_CHECK_ARG(K % 8 == 0, "gemm: K must be a multiple of 8 (got %d)", K);
   TFIMM_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0, "gemm: bias must be 16-byte aligned");
   TFIMM_CHECK_ARG(gamma == nullptr || (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0, "gemm: gamma must be 16-byte aligned");
-  TFIMM_CHECK_ARG(ln_stats == nullptr || (ln_parts > 0 && ln_colsum != nullptr &&
-                                          (reinterpret_cast<uintptr_t>(ln_colsum) & 15u) == 0 &&
-                                          (reinterpret_cast<uintptr_t>(ln_stats) & 7u) == 0),
-                  "gemm: LayerNorm folding needs ln_parts > 0 and a 16-byte aligned colsum");
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.gamma = gamma; p.act = act; p.has_res = residual != nullptr ? 1 : 0; p.act_post = act_post;
-  p.ln_stats = ln_stats; p.ln_colsum = ln_colsum; p.ln_parts = ln_parts; p.ln_inv_dim = 1.0f / (float)K;
-  p.ln_eps = ln_eps;
-  p.emit_bf16 = reinterpret_cast<__nv_bfloat16*>(emit_bf16); p.ld_emit = ld_emit; p.emit_stats = emit_stats;
   // force_block_n: 0 = choose; 64/128/256 = one-CTA kernel with that tile width; 2 = CTA-pair 256x256 kernel
   const bool pair = force_block_n == 2 || (force_block_n == 0 && prefer_pair(M, N));
   int bn = pair ? 256 : (force_block_n > 0 ? force_block_n : pick_block_n(M, N));
-  if (!pair && bn == 256 && emit_stats != nullptr && force_block_n == 0) bn = 128;  // room for the copy slabs
-  if (emit_stats != nullptr) {
-    const int ch = out_dtype == kBF16 ? 64 : 32;
-    TFIMM_CHECK_ARG(N % ch == 0, "gemm: statistics emission needs N %% %d == 0 (got %d)", ch, N);
-    // chunk groups per tile x N tiles (the CTA-pair kernel's bf16 instance runs four epilogue groups)
-    const int parts = (pair && out_dtype == kBF16 ? 4 : 2) * ((N + bn - 1) / bn);
-    TFIMM_CHECK_ARG(emit_parts == parts,
-                    "gemm: emit_parts must be %d for this shape (got %d); tfimm_b200_gemm_stat_parts gives the "
-                    "count for an fp32 C", parts, emit_parts);
-    TFIMM_CHECK_ARG(emit_bf16 == nullptr || (out_dtype == kF32 && ld_emit % 8 == 0 &&
-                                             (reinterpret_cast<uintptr_t>(emit_bf16) & 15u) == 0),
-                    "gemm: the bf16 copy needs an fp32 C, ld_emit %% 8 == 0 and a 16-byte aligned pointer");
-  }
   if (pair) return gemm_bf16_pair(A, lda, W, ldw, residual, ldr, C, ldc, p, out_dtype, stream);
 #define TFIMM_GEMM_CASE(BN)                                                                         \
   case BN:                                                                                          \
@@ -449,14 +408,6 @@ int conv_bf16_dispatch(const void* x, const void* W, int ldw, const float* bias,
   }
 #undef TFIMM_CONV_CASE
   return kInvalidArgument;
-}
-
-// Number of per-row partial statistics a statistics-emitting GEMM of this shape writes (see gemm_bf16_dispatch).
-int gemm_bf16_stat_parts(int M, int N, int force_block_n) {
-  const bool pair = force_block_n == 2 || (force_block_n == 0 && prefer_pair(M, N));
-  int bn = pair ? 256 : (force_block_n > 0 ? force_block_n : pick_block_n(M, N));
-  if (!pair && bn == 256 && force_block_n == 0) bn = 128;  // same rule as gemm_bf16_dispatch
-  return 2 * ((N + bn - 1) / bn);
 }
 
 }  // namespace tfimm

@@ -166,30 +166,6 @@ int dispatch_ln(int in_dtype, int out_dtype, const float* gamma, const float* be
 }
 
 
-// Entry point of a LayerNorm-folded stream (see GemmParams in gemm_epilogue.cuh): bf16 copy of fp32 rows plus the
-// per-row (sum, sum of squares) statistics as ONE partial.  One warp per row.
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-row_stats_cast_kernel(const float* __restrict__ x, long in_stride, __nv_bfloat16* __restrict__ out, long out_stride,
-                      float* __restrict__ stats, long rows, int C) {
-  const int lane = threadIdx.x & 31;
-  const long row = (long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  float s = 0.f, q = 0.f;
-  for (int c = lane * 8; c < C; c += 256) {
-    float v[8];
-    ld8(x + row * in_stride + c, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s += v[j];
-      q = fmaf(v[j], v[j], q);
-    }
-    st8(out + row * out_stride + c, v);
-  }
-  s = warp_sum(s);
-  q = warp_sum(q);
-  if (lane == 0) reinterpret_cast<float2*>(stats)[row] = make_float2(s, q);
-}
-
 }  // namespace
 
 int layernorm_rows(const void* x, int in_dtype, long in_stride, const float* gamma, const float* beta,
@@ -215,17 +191,6 @@ int patch_merge_ln(const void* x, int in_dtype, const float* gamma, const float*
                   "patch_merge_ln: need even H, W and C%%8==0 (H=%d W=%d C=%d)", H, W, C);
   PatchMergeRows map{x, out, H, W, C};
   return dispatch_ln(in_dtype, out_dtype, gamma, beta, (long)B * (H / 2) * (W / 2), 4 * C, eps, map, stream);
-}
-
-int row_stats_cast(const float* x, long in_stride, void* out_bf16, long out_stride, float* stats, long rows, int C,
-                   cudaStream_t stream) {
-  TFIMM_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "row_stats_cast: need rows>0 and C%%8==0 (rows=%ld C=%d)", rows, C);
-  TFIMM_CHECK_ARG(in_stride % 8 == 0 && out_stride % 8 == 0, "row_stats_cast: strides must be multiples of 8 elements");
-  const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  row_stats_cast_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(x, in_stride, reinterpret_cast<__nv_bfloat16*>(out_bf16),
-                                                                   out_stride, stats, rows, C);
-  TFIMM_LAUNCH_OK("row_stats_cast_kernel");
-  return kOk;
 }
 
 }  // namespace tfimm

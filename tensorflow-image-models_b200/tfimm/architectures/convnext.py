@@ -127,10 +127,6 @@ class ConvNeXt(Model):
                     fc2_b=self._vec(f"{p}/mlp/fc2/bias"),
                     ls=self._vec(f"{p}/gamma"),
                 ))
-                if self.precision == "bf16" and dim % 32 == 0:
-                    # norm -> fc1 with the LayerNorm folded into the GEMM (dwconv7_stats + gemm(..., ln=...))
-                    st["blocks"][-1]["fc1_ln"] = self._ln_folded_dense(
-                        f"{p}/mlp/fc1/kernel", f"{p}/mlp/fc1/bias", f"{p}/norm/gamma", f"{p}/norm/beta")
             P["stages"].append(st)
         P["head_n"] = (self._vec("head/norm/gamma"), self._vec("head/norm/beta"))
         if c.nb_classes > 0:
@@ -151,11 +147,6 @@ class ConvNeXt(Model):
         xs = ops.layernorm(y, *P["stem_n"], eps, rdt)  # residual stream (B*H*W, C) fp32
         if return_features:
             features["stem"] = xs.view(B, H, W, -1).clone()
-        # Opt-in (TFIMM_B200_CONVNEXT_FOLD=1): LayerNorm folded into fc1 and a cluster-free depthwise kernel.  Measured
-        # slower than the fused dwconv+LayerNorm cluster kernel (18.2 vs 17.1 ms per ConvNeXt-B step): the depthwise
-        # kernel gains only 7 % without its LayerNorm phases while the K <= 512 GELU GEMMs, whose epilogue is FMA-pipe
-        # bound, pay 30 % for the fold.
-        fold = self.precision == "bf16" and os.environ.get("TFIMM_B200_CONVNEXT_FOLD", "0") == "1"
         for j, st in enumerate(P["stages"]):
             dim = st["dim"]
             if j > 0:
@@ -165,15 +156,8 @@ class ConvNeXt(Model):
                 if return_features:
                     features[f"stage_{j}/downsample"] = xs.view(B, H, W, dim).clone()
             for k, blk in enumerate(st["blocks"]):
-                if fold and "fc1_ln" in blk:
-                    # the depthwise kernel emits the RAW bf16 result + per-pixel partial (sum, sumsq); the LayerNorm
-                    # is applied in fc1's epilogue: LN(x) W = rstd * (x (gamma W) - mean * colsum) + (b + beta W)
-                    raw, stats = ops.dwconv7_stats(xs.view(B, H, W, dim), blk["dw_w"], blk["dw_b"])
-                    wf, cs, bf = blk["fc1_ln"]
-                    hid = ops.gemm(raw.view(-1, dim), wf, bias=bf, act=c.act_layer, ln=(stats, cs, eps))
-                else:
-                    h = ops.dwconv_ln(xs.view(B, H, W, dim), blk["dw_w"], blk["dw_b"], *blk["n"], eps, adt)
-                    hid = ops.gemm(h, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)
+                h = ops.dwconv_ln(xs.view(B, H, W, dim), blk["dw_w"], blk["dw_b"], *blk["n"], eps, adt)
+                hid = ops.gemm(h, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)
                 ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], gamma=blk["ls"], residual=xs, out=xs)
                 if return_features:
                     features[f"stage_{j}/block_{k}"] = xs.view(B, H, W, dim).clone()

@@ -16,7 +16,6 @@ The residual stream stays in fp32 (bf16 would add ~2^-9 relative noise 24 times)
 operand is bf16 with fp32 accumulation.  ``precision="fp32"`` runs the same graph with fp32 SIMT
 kernels and matches the oracle to ~1e-6.
 """
-import os
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Optional, Tuple, Union
@@ -85,6 +84,8 @@ class ViTConfig(ModelConfig):
 class ViT(Model):
     cfg_class = ViTConfig
     accepts_uint8 = True
+    # Graph-level optimisation of the bf16 fast path (see forward_features); output-preserving, on by default.
+    prune_last_block = True
 
     def __init__(self, cfg: ViTConfig, *args, **kwargs):
         if isinstance(cfg, dict):
@@ -165,13 +166,6 @@ class ViT(Model):
                 fc2_w=self._dense_weight(f"{p}/mlp/fc2/kernel"),
                 fc2_b=self._vec(f"{p}/mlp/fc2/bias"),
             ))
-            if self.precision == "bf16":
-                # norm1 -> qkv and norm2 -> fc1 with the LayerNorm folded into the GEMM (no LN pass at all)
-                P["blocks"][-1]["qkv_ln"] = self._ln_folded_dense(
-                    f"{p}/attn/qkv/kernel", f"{p}/attn/qkv/bias" if c.qkv_bias else None,
-                    f"{p}/norm1/gamma", f"{p}/norm1/beta")
-                P["blocks"][-1]["fc1_ln"] = self._ln_folded_dense(
-                    f"{p}/mlp/fc1/kernel", f"{p}/mlp/fc1/bias", f"{p}/norm2/gamma", f"{p}/norm2/beta")
         P["norm"] = (self._vec("norm/gamma"), self._vec("norm/beta"))
         if c.representation_size:
             P["pre_w"] = self._dense_weight("pre_logits/fc/kernel")
@@ -214,24 +208,10 @@ class ViT(Model):
         eps, adt = P["eps"], self.act_dtype
         if return_features:
             features["patch_embedding"] = xs.view(B, T, D).clone()
-        # LayerNorm folded into the qkv / fc1 GEMMs (tfimm_b200_gemm_bf16_ln).  Opt-in: it removes the LN passes
-        # (-3.7 GB of HBM traffic per ViT-B step) but the K = 768 GEMMs are epilogue-bound, and on a power-capped
-        # B200 the extra epilogue work costs as much as the LN kernels did.
-        fold = self.precision == "bf16" and os.environ.get("TFIMM_B200_LN_FOLD", "0") == "1"
-        if fold:
-            # the residual stream keeps a bf16 shadow (A operand of the folded GEMMs) and per-row partial
-            # (sum, sumsq) statistics, both refreshed by the epilogue of every GEMM that updates the stream
-            x16, st = ops.row_stats_cast(xs)
-            st_blk = torch.empty((B * T, ops.gemm_stat_parts(B * T, D), 2), device=xs.device, dtype=torch.float32)
-        prune_last = (not return_features and self.precision == "bf16" and dh == 64 and T <= 512
-                      and os.environ.get("TFIMM_B200_VIT_PRUNE", "1") != "0")
+        prune_last = not return_features and self.precision == "bf16" and dh == 64 and T <= 512 and self.prune_last_block
         for j, blk in enumerate(P["blocks"]):
-            if fold:
-                wf, cs, bf = blk["qkv_ln"]
-                qkv = ops.gemm(x16, wf, bias=bf, ln=(st, cs, eps))
-            else:
-                h = ops.layernorm(xs, *blk["n1"], eps, adt)
-                qkv = ops.gemm(h, blk["qkv_w"], bias=blk["qkv_b"])
+            h = ops.layernorm(xs, *blk["n1"], eps, adt)
+            qkv = ops.gemm(h, blk["qkv_w"], bias=blk["qkv_b"])
             if return_features:
                 probs = torch.empty((B, Hh, T, T), device=xs.device, dtype=torch.float32)
                 ops.attention(ops.cast(qkv, torch.float32), B, T, Hh, dh, scale, probs=probs)
@@ -239,7 +219,7 @@ class ViT(Model):
             if prune_last and j == len(P["blocks"]) - 1:
                 # Last block: only the class (and distillation) token rows reach the head (vit.py:452-464), so
                 # attention, proj, norm2 and the MLP run on those B * nq rows only; keys / values above came from
-                # every token.  Same arithmetic per row, 6-7 % of a ViT-B step.  TFIMM_B200_VIT_PRUNE=0 disables.
+                # every token.  Same arithmetic per row, 6-7 % of a ViT-B step.  ``model.prune_last_block = False`` disables.
                 nq = 2 if c.distilled else 1
                 a = ops.attention_cls(qkv, B, T, Hh, dh, scale, nq)
                 x3 = xs.view(B, T, D)
@@ -251,17 +231,10 @@ class ViT(Model):
                     ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], residual=xi, out=xi)
                 continue
             a = ops.attention(qkv, B, T, Hh, dh, scale)
-            if fold:
-                st = st_blk
-                ops.gemm(a, blk["proj_w"], bias=blk["proj_b"], residual=xs, out=xs, emit=(x16, st))
-                wf, cs, bf = blk["fc1_ln"]
-                hid = ops.gemm(x16, wf, bias=bf, act=c.act_layer, ln=(st, cs, eps))
-                ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], residual=xs, out=xs, emit=(x16, st))
-            else:
-                ops.gemm(a, blk["proj_w"], bias=blk["proj_b"], residual=xs, out=xs)
-                h = ops.layernorm(xs, *blk["n2"], eps, adt)
-                hid = ops.gemm(h, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)
-                ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], residual=xs, out=xs)
+            ops.gemm(a, blk["proj_w"], bias=blk["proj_b"], residual=xs, out=xs)
+            h = ops.layernorm(xs, *blk["n2"], eps, adt)
+            hid = ops.gemm(h, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)
+            ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], residual=xs, out=xs)
             if return_features:
                 features[f"block_{j}"] = xs.view(B, T, D).clone()
         x3 = xs.view(B, T, D)

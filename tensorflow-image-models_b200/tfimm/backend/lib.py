@@ -28,11 +28,7 @@ _F = _c.c_float
 # name -> argtypes; restype is int (status) unless listed in _SPECIAL
 SIGNATURES = {
     "tfimm_b200_gemm_bf16": [_P, _I, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "tfimm_b200_gemm_bf16_ln": [_P, _I, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I,
-                                _P, _I, _P, _F, _P, _I, _P, _I, _P],
     "tfimm_b200_conv_bf16": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "tfimm_b200_dwconv7_stats": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "tfimm_b200_row_stats_cast": [_P, _L, _P, _L, _P, _L, _I, _P],
     "tfimm_b200_gemm_f32": [_P, _I, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "tfimm_b200_layernorm": [_P, _I, _L, _P, _P, _P, _I, _L, _L, _I, _F, _P],
     "tfimm_b200_layernorm_patch2x2": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
@@ -61,8 +57,6 @@ _SPECIAL = {
     "tfimm_b200_version": ([], _c.c_char_p),
     "tfimm_b200_last_error": ([], _c.c_char_p),
     "tfimm_b200_sm_count": ([], _I),
-    "tfimm_b200_gemm_stat_parts": ([_I, _I, _I], _I),
-    "tfimm_b200_dwconv7_stats_parts": ([_I], _I),
 }
 
 _lib = None

@@ -53,7 +53,7 @@ def _call(name, *args, flops=0.0, nbytes=0.0):
         e0.record()
         _lib.check(fn(*args), name)
         e1.record()
-        trace.append((name.replace("tfimm_b200_", "").replace("gemm_bf16_ln", "gemm_bf16").replace("conv_bf16", "gemm_bf16").replace("dwconv7_stats", "dwconv_ln"), e0, e1, float(flops),
+        trace.append((name.replace("tfimm_b200_", "").replace("conv_bf16", "gemm_bf16"), e0, e1, float(flops),
                       float(nbytes)))
     else:
         _lib.check(fn(*args), name)
@@ -71,35 +71,10 @@ def act_code(act) -> int:
         raise ValueError(f"Unknown activation: {act}.")
 
 
-def gemm_stat_parts(M, N, block_n=0) -> int:
-    """Number of per-row partial statistics a statistics-emitting bf16 GEMM of this shape writes."""
-    return int(_lib.load().tfimm_b200_gemm_stat_parts(int(M), int(N), int(block_n)))
-
-
-def row_stats_cast(x, out=None, stats=None):
-    """fp32 rows -> (bf16 copy, [rows,1,2] (sum, sum of squares)): entry of a LayerNorm-folded stream."""
-    _cuda(x, out, stats)
-    rows, C = x.shape
-    assert x.dtype == torch.float32 and x.stride(1) == 1
-    if out is None:
-        out = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16)
-    if stats is None:
-        stats = torch.empty((rows, 1, 2), device=x.device, dtype=torch.float32)
-    _call("tfimm_b200_row_stats_cast", x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), stats.data_ptr(),
-          rows, C, _stream(), nbytes=_nbytes(x, out))
-    return out, stats
-
-
 def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dtype=None, block_n=0,
-         act_after_residual=False, ln=None, emit=None):
+         act_after_residual=False):
     """out = residual + gamma * act(a @ w.T + bias)  (act_after_residual: act(residual + gamma*(...))).
-    a:(M,K), w:(N,K); bf16 -> tcgen05, fp32 -> SIMT.
-
-    bf16 only -- LayerNorm folding (tfimm_b200_gemm_bf16_ln):
-      ln=(stats, colsum, eps): ``a`` holds raw rows, ``w`` has the LN gamma folded in, ``bias`` the beta term;
-          stats is the producer's [M, parts, 2] partial (sum, sumsq) tensor.
-      emit=(copy_bf16 or None, stats): also write a bf16 copy of ``out`` (fp32 out only) and this GEMM's per-row
-          partial statistics, stats: [M, gemm_stat_parts(M, N, block_n), 2]."""
+    a:(M,K), w:(N,K); bf16 -> tcgen05, fp32 -> SIMT."""
     _cuda(a, w, bias, gamma, residual, out)
     M, K = a.shape
     N = w.shape[0]
@@ -116,28 +91,10 @@ def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dty
     ldr = residual.stride(0) if residual is not None else 0
     if a.dtype == torch.bfloat16:
         assert w.dtype == torch.bfloat16
-        if ln is None and emit is None:
-            _call("tfimm_b200_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
-                  _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
-                  int(bool(act_after_residual)), _code(out), block_n, _stream(), flops=2.0 * M * N * K,
-                  nbytes=_nbytes(a, w, out, residual))
-        else:
-            ln_stats, ln_colsum, ln_eps = ln if ln is not None else (None, None, 0.0)
-            copy, est = emit if emit is not None else (None, None)
-            _cuda(ln_stats, ln_colsum, copy, est)
-            if ln_stats is not None:
-                assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.shape[0] == M
-                assert ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N
-            if est is not None:
-                assert est.dtype == torch.float32 and est.is_contiguous() and est.shape[0] == M and est.shape[2] == 2
-            if copy is not None:
-                assert copy.dtype == torch.bfloat16 and copy.shape == (M, N) and copy.stride(1) == 1
-            _call("tfimm_b200_gemm_bf16_ln", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
-                  _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
-                  int(bool(act_after_residual)), _code(out), block_n,
-                  _ptr(ln_stats), 0 if ln_stats is None else ln_stats.shape[1], _ptr(ln_colsum), float(ln_eps),
-                  _ptr(copy), 0 if copy is None else copy.stride(0), _ptr(est), 0 if est is None else est.shape[1],
-                  _stream(), flops=2.0 * M * N * K, nbytes=_nbytes(a, w, out, residual, copy))
+        _call("tfimm_b200_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+              _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
+              int(bool(act_after_residual)), _code(out), block_n, _stream(), flops=2.0 * M * N * K,
+              nbytes=_nbytes(a, w, out, residual))
     else:
         assert a.dtype == torch.float32 and w.dtype == torch.float32 and out.dtype == torch.float32
         _call("tfimm_b200_gemm_f32", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
@@ -174,22 +131,6 @@ def attention_cls(qkv, B, T, H, dh, scale, nq=1):
     _call("tfimm_b200_attention_cls_bf16", qkv.data_ptr(), out.data_ptr(), B, T, H, dh, nq, float(scale), _stream(),
           flops=4.0 * B * H * nq * T * dh, nbytes=2.0 * B * T * 2 * H * dh)
     return out
-
-
-def dwconv7_stats(x, wgt, bias):
-    """ZeroPad(3) + depthwise 7x7 + bias of an fp32 NHWC tensor -> (raw result bf16 (B,H,W,C), per-pixel partial
-    (sum, sumsq) statistics (B*H*W, parts, 2) fp32) for a LayerNorm-folded GEMM."""
-    _cuda(x, wgt, bias)
-    B, H, W, C = x.shape
-    assert x.dtype == torch.float32 and x.is_contiguous() and wgt.shape == (49, C)
-    parts = int(_lib.load().tfimm_b200_dwconv7_stats_parts(C))
-    if parts <= 0:
-        raise ValueError(f"dwconv7_stats needs C % 32 == 0 (C={C})")
-    out = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
-    stats = torch.empty((B * H * W, parts, 2), device=x.device, dtype=torch.float32)
-    _call("tfimm_b200_dwconv7_stats", x.data_ptr(), wgt.data_ptr(), bias.data_ptr(), out.data_ptr(), stats.data_ptr(),
-          B, H, W, C, _stream(), flops=2.0 * 49 * x.numel(), nbytes=_nbytes(x, out, stats))
-    return out, stats
 
 
 def layernorm(x, gamma, beta, eps, out_dtype, out=None):

@@ -1,33 +1,40 @@
 """Cold-path (load-time) resampling of position embeddings.
 
 ``interpolate_pos_embeddings`` mirrors tfimm/layers/transformers.py:13-47, which calls
-``tf.image.resize(method="bicubic")``.  TF2's bicubic resize is the Keys cubic kernel with
-A = -0.5, half-pixel centres, no antialiasing, and -- unlike OpenCV / PyTorch -- taps that fall
-outside the image are dropped and the remaining weights renormalised
-(tensorflow/core/kernels/image/scale_and_translate_op.cc, ComputeSpans).  It runs once per
-weight load on a (1, N, D) tensor, so it is plain torch on whatever device the weight lives on.
+``tf.image.resize(method="bicubic")``.  With ``antialias=False`` that dispatches to the ``ResizeBicubic`` op
+with ``half_pixel_centers=True`` (tensorflow/core/kernels/image/resize_bicubic_op.cc): Keys cubic kernel with
+A = -0.5 read from a 1024-step table (the fractional source offset is rounded to the table grid), float32
+source coordinate ``(o + 0.5) * scale - 0.5`` and -- unlike OpenCV / PyTorch -- taps that fall outside the image
+get weight zero with the remaining weights renormalised.  It runs once per weight load on a (1, N, D) tensor, so
+it is plain torch on whatever device the weight lives on.
 """
 from typing import Tuple
 
+import numpy as np
 import torch
 
-
-def _keys_cubic(x: torch.Tensor) -> torch.Tensor:
-    a = -0.5
-    x = x.abs()
-    near = ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0
-    far = ((a * x - 5.0 * a) * x + 8.0 * a) * x - 4.0 * a
-    return torch.where(x <= 1.0, near, torch.where(x < 2.0, far, torch.zeros_like(x)))
+_TABLE = 1024
+_A = -0.5
 
 
 def _resize_matrix(n_in: int, n_out: int, dtype, device) -> torch.Tensor:
     """(n_out, n_in) interpolation matrix of TF2's bicubic resize along one axis."""
-    scale = n_in / n_out
-    centers = (torch.arange(n_out, dtype=torch.float64, device=device) + 0.5) * scale
-    src = torch.arange(n_in, dtype=torch.float64, device=device) + 0.5
-    w = _keys_cubic(src[None, :] - centers[:, None])  # kernel scale 1 (no antialias)
-    w = w / w.sum(dim=1, keepdim=True)
-    return w.to(dtype)
+    x = np.arange(_TABLE + 1, dtype=np.float64) / _TABLE
+    near = (((_A + 2.0) * x - (_A + 3.0)) * x * x + 1.0).astype(np.float32)
+    x1 = x + 1.0
+    far = (((_A * x1 - 5.0 * _A) * x1 + 8.0 * _A) * x1 - 4.0 * _A).astype(np.float32)
+    scale = np.float32(n_in) / np.float32(n_out)
+    src = (np.arange(n_out, dtype=np.float32) + np.float32(0.5)) * scale - np.float32(0.5)
+    base = np.floor(src).astype(np.int64)
+    off = np.rint((src - base.astype(np.float32)) * np.float32(_TABLE)).astype(np.int64)
+    w = np.zeros((n_out, n_in), dtype=np.float32)
+    rows = np.arange(n_out)
+    for k, tap in ((-1, far[off]), (0, near[off]), (1, near[_TABLE - off]), (2, far[_TABLE - off])):
+        idx = base + k
+        ok = (idx >= 0) & (idx < n_in)
+        np.add.at(w, (rows[ok], idx[ok]), tap[ok])
+    w = w / w.sum(axis=1, keepdims=True, dtype=np.float32)
+    return torch.from_numpy(w).to(device=device, dtype=dtype)
 
 
 def tf_bicubic_resize(images: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:

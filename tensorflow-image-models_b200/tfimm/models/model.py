@@ -188,23 +188,6 @@ class Model:
             w2 = torch.nn.functional.pad(w2, (0, Kpad - K))
         return w2.to(self.act_dtype).contiguous()
 
-    def _ln_folded_dense(self, w_key: str, b_key: Optional[str], gamma_key: str, beta_key: str):
-        """LayerNormalization followed by Dense, folded for ``ops.gemm(..., ln=...)``:
-        ``LN(x) W + b = rstd * (x (gamma*W) - mean * colsum) + (b + beta W)``.
-        Returns (W' [out][K] bf16 with gamma folded in, colsum of the ROUNDED W' in fp32, bias')."""
-        w = self.params[w_key]
-        out = w.shape[-1]
-        w2 = w.reshape(-1, out).t().float()  # (out, K)
-        if w2.shape[1] % 8 != 0:
-            raise ValueError(f"{w_key}: LayerNorm folding needs K % 8 == 0")
-        gamma, beta = self._vec(gamma_key), self._vec(beta_key)
-        wf = (w2 * gamma[None, :]).to(torch.bfloat16).contiguous()
-        colsum = wf.float().sum(dim=1).contiguous()
-        bias = w2 @ beta
-        if b_key is not None:
-            bias = bias + self._vec(b_key)
-        return wf, colsum, bias.contiguous()
-
     def _vec(self, key: str) -> torch.Tensor:
         return self.params[key].reshape(-1).float().contiguous()
 

@@ -30,12 +30,17 @@ def pytorch_key(weight_key: str) -> str:
 
 
 def _to_engine_layout(array: np.ndarray, key: str, target_shape: Tuple[int, ...]) -> np.ndarray:
+    """Layout rule of the reference (tfimm/utils/timm.py:76-90, 164-188): the TRANSPOSE is chosen from the rank of the
+    TF-side variable -- rank-4 ``kernel`` / ``depthwise_kernel`` take ``(2, 3, 1, 0)`` of the PyTorch tensor (CONV2D),
+    every other kernel takes the full axis reversal (SIMPLE, so a conv-as-linear ``(out, in, 1, 1)`` checkpoint
+    becomes ``(1, 1, in, out)`` and squeezes to ``(in, out)``) -- then a missing / extra leading axis is expanded /
+    squeezed and a final same-size reshape reconciles e.g. ``cls_token`` or depthwise ``(1, k, k, C) -> (k, k, C, 1)``."""
     leaf = key.rsplit("/", 1)[-1]
     if leaf in ("kernel", "depthwise_kernel"):
-        if len(target_shape) == 4 and array.ndim == 4:
+        if len(target_shape) == 4:
             array = np.transpose(array, (2, 3, 1, 0))
-        elif array.ndim == 2:
-            array = array.T
+        else:
+            array = np.transpose(array)
     if array.ndim > len(target_shape):
         array = np.squeeze(array)
     elif array.ndim < len(target_shape):

@@ -109,27 +109,6 @@ def test_every_registration_constructs():
         assert m.count_params() > 0, name
 
 
-def test_layernorm_fold_algebra():
-    """Host side of tfimm_b200_gemm_bf16_ln: LN(x) W + b == rstd * (x (gamma W) - mean * colsum) + (b + beta W)."""
-    m = tfimm.create_model("vit_tiny_patch16_224", device="cpu", nb_blocks=1)
-    g = torch.Generator().manual_seed(0)
-    for key in ("blocks/0/norm1/gamma", "blocks/0/norm1/beta", "blocks/0/attn/qkv/kernel", "blocks/0/attn/qkv/bias"):
-        m.params[key] = torch.randn(m.params[key].shape, generator=g)
-    m.precision = "bf16"
-    wf, colsum, bias = m._ln_folded_dense("blocks/0/attn/qkv/kernel", "blocks/0/attn/qkv/bias",
-                                          "blocks/0/norm1/gamma", "blocks/0/norm1/beta")
-    x = torch.randn(5, 192, generator=g) * 2 + 0.3
-    eps = 1e-6
-    mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
-    rstd = torch.rsqrt(var + eps)
-    folded = rstd * (x @ wf.float().t() - mean * colsum) + bias
-    ref = torch.nn.functional.layer_norm(x, (192,), m.params["blocks/0/norm1/gamma"], m.params["blocks/0/norm1/beta"],
-                                         eps) @ m.params["blocks/0/attn/qkv/kernel"] + m.params["blocks/0/attn/qkv/bias"]
-    # the only difference is the bf16 rounding of gamma * W
-    assert (folded - ref).abs().max() < 2.0 ** -7 * ref.abs().max()
-    assert wf.dtype == torch.bfloat16 and wf.shape == (576, 192) and colsum.shape == (576,)
-
-
 def test_no_cpu_fallback():
     from tfimm.backend.lib import KernelLibraryError
 

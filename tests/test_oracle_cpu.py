@@ -127,10 +127,10 @@ def test_tf_bicubic_resize_properties():
     img = torch.randn(1, 5, 7, 3, generator=g, dtype=torch.float64)
     assert (tf.resize_bicubic(img, (5, 7)) - img).abs().max() < 1e-12          # identity at native size
     const = torch.full((1, 4, 4, 1), 2.5, dtype=torch.float64)
-    assert (tf.resize_bicubic(const, (9, 6)) - 2.5).abs().max() < 1e-12         # weights renormalised at the border
+    assert (tf.resize_bicubic(const, (9, 6)) - 2.5).abs().max() < 1e-6          # weights renormalised (in float32)
     up = tf.resize_bicubic(img, (10, 14))
     from tfimm.layers import tf_bicubic_resize
-    assert (tf_bicubic_resize(img, (10, 14)) - up).abs().max() < 1e-12          # engine and oracle agree
+    assert (tf_bicubic_resize(img, (10, 14)) - up).abs().max() < 1e-6           # engine and oracle agree (fp32 weights)
 
 
 # ------------------------------------------------------------------------------------------ parameter counts
@@ -378,11 +378,18 @@ def test_oracle_reproduces_committed_golden_logits(fixture):
     cfg = tfimm.models.model_config(meta["model"])
     cfg = type(cfg)(**{**cfg.__dict__, **meta["overrides"]})
     w = params.random_params(mod.param_shapes(cfg), seed=meta["seed"])
-    x = params.test_images(meta["batch"], *cfg.input_size, cfg.in_channels)
-    assert np.array_equal(x.numpy(), data["images"])
+    x = params.test_images(meta["batch"], *cfg.input_size, cfg.in_channels, seed=meta.get("images_seed", 2021))
+    if "images" in data.files:
+        assert np.array_equal(x.numpy(), data["images"])
+    if fixture.startswith("full_"):
+        x, want = x[:1], data["logits"][:1]  # full-size BASELINE configs: one image keeps the CPU suite short
+    else:
+        want = data["logits"]
     with torch.no_grad():
         y = mod.forward(cfg, w, x)
-    assert nerr(y, torch.from_numpy(data["logits"])) < 1e-5
+    # the stored logits were computed by the reference's own code on the TF shim (tools/make_golden.py)
+    assert "reference" in meta.get("source", "")
+    assert nerr(y, torch.from_numpy(want)) < 5e-6
 
 
 def test_pytorch_state_dict_ingestion_reproduces_torchvision_resnet():

@@ -1,4 +1,4 @@
-"""GEMM micro-benchmark: python tools/bench_gemm.py M N K [act] [out=bf16|f32] [res=0|1] [block_n] [ln=0|1] [emit=0|1]
+"""GEMM micro-benchmark: python tools/bench_gemm.py M N K [act] [out=bf16|f32] [res=0|1] [block_n]
 Prints the device time per launch (CUDA events, 20 launches after warm-up) and the achieved TFLOP/s."""
 import sys
 from pathlib import Path
@@ -17,23 +17,13 @@ def main():
     out_dtype = torch.float32 if len(sys.argv) > 5 and sys.argv[5] == "f32" else torch.bfloat16
     res = len(sys.argv) > 6 and sys.argv[6] == "1"
     block_n = int(sys.argv[7]) if len(sys.argv) > 7 else 0
-    use_ln = len(sys.argv) > 8 and sys.argv[8] == "1"
-    use_emit = len(sys.argv) > 9 and sys.argv[9] == "1"
     g = torch.Generator(device="cuda").manual_seed(0)
     a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
     w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
     bias = torch.randn(N, device="cuda", generator=g)
     x = torch.randn(M, N, device="cuda", generator=g).to(out_dtype)
-    kw = {}
-    if use_ln:
-        st = torch.rand(M, 6, 2, device="cuda") + 1.0
-        kw["ln"] = (st, torch.randn(N, device="cuda"), 1e-6)
-    if use_emit:
-        parts = ops.gemm_stat_parts(M, N, block_n)
-        copy = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if out_dtype == torch.float32 else None
-        kw["emit"] = (copy, torch.empty(M, parts, 2, device="cuda"))
-    fn = (lambda: ops.gemm(a, w, bias=bias, act=act, residual=x, out=x, block_n=block_n, **kw)) if res else \
-         (lambda: ops.gemm(a, w, bias=bias, act=act, out=x, block_n=block_n, **kw))
+    fn = (lambda: ops.gemm(a, w, bias=bias, act=act, residual=x, out=x, block_n=block_n)) if res else \
+         (lambda: ops.gemm(a, w, bias=bias, act=act, out=x, block_n=block_n))
     for _ in range(5):
         fn()
     torch.cuda.synchronize()
@@ -45,7 +35,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
-    print(f"gemm M={M} N={N} K={K} act={act} out={str(out_dtype)[6:]} res={int(res)} block_n={block_n} ln={int(use_ln)} emit={int(use_emit)}: "
+    print(f"gemm M={M} N={N} K={K} act={act} out={str(out_dtype)[6:]} res={int(res)} block_n={block_n}: "
           f"{us:.1f} us  {2.0 * M * N * K / us * 1e-6:.0f} TFLOP/s")
 
 
