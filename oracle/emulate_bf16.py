@@ -353,7 +353,7 @@ def emulated_ops():
     from tfimm.backend import ops
 
     missing = [n for n in dir(ops) if callable(getattr(ops, n)) and not n.startswith("_") and n not in _EMULATED
-               and n not in ("act_code", "same_pad", "conv_geometry", "Optional") and
+               and n not in ("act_code", "same_pad", "conv_geometry", "attention_bf16_supported", "Optional") and
                getattr(getattr(ops, n), "__module__", "") == ops.__name__]
     if missing:
         raise RuntimeError(f"oracle/emulate_bf16.py has no emulation for ops.{missing}")

@@ -25,17 +25,19 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int sm_count() {
-  static int cached = -1;
-  if (cached < 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return 0;
-    }
-    cached = n;
+  static int cached[64] = {0};
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
   }
-  return cached;
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  if (dev >= 0 && dev < 64) cached[dev] = n;
+  return n;
 }
 
 // implemented in the other translation units

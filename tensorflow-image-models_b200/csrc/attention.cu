@@ -200,11 +200,9 @@ int launch_vit_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, in
     return kUnsupported;
   }
   auto kernel = vit_attention_bf16_kernel<NW, TPW>;
-  static size_t attr = 0;
-  if (smem > attr) {
-    TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_device(attr_devs))
+    TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   dim3 grid((N + ROWS - 1) / ROWS, H, B);
   kernel<<<grid, NW * 32, smem, stream>>>(qkv, out, N, H, scale * 1.4426950408889634f);
   TFIMM_LAUNCH_OK("vit_attention_bf16_kernel");
@@ -295,7 +293,9 @@ int attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, floa
   if (N <= 256 && mode == 1) return attention_bf16_tc(qkv, out, B, N, H, scale, stream);
   auto q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   auto o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (N <= 128) return launch_vit_attention<4, 2>(q, o, B, N, H, scale, stream);
+  // resident K/V + one query tile per CTA must fit 227 KB: 224-row tiles up to N = 784, 128-row tiles up to N = 832
+  // (vit_base_patch8_224 has N = 785); longer sequences are kUnsupported (the host falls back to the fp32 kernel)
+  if (N <= 128 || N > 784) return launch_vit_attention<4, 2>(q, o, B, N, H, scale, stream);
   return launch_vit_attention<7, 2>(q, o, B, N, H, scale, stream);
 }
 

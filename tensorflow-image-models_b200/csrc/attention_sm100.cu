@@ -491,10 +491,9 @@ int attention_bf16_tc2(const void* qkv, void* out, int B, int N, int H, float sc
     int st;
     if ((st = make_tmap(&to, out, kBF16, 3, dims, strides, box, "attention out")) != kOk) return st;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2SmemBytes));
-    attr_set = true;
   }
   const int items = B * H;
   const int grid = items < sm_count() ? items : sm_count();
@@ -524,10 +523,9 @@ int attention_bf16_tc(const void* qkv, void* out, int B, int N, int H, float sca
     int st;
     if ((st = make_tmap(&to, out, kBF16, 3, dims, strides, box, "attention out")) != kOk) return st;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
   }
   dim3 grid((N + kQRows - 1) / kQRows, H, B);
   vit_attention_tc_kernel<<<grid, 128, kSmemBytes, stream>>>(tq, tkv, to, N, H, scale * 1.4426950408889634f);

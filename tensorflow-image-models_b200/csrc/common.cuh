@@ -61,7 +61,18 @@ enum Act : int {
   kActSigmoid = 6,
 };
 
-int sm_count();
+int sm_count();  // of the CURRENT device (cached per device)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: `mask` (one static per kernel
+// instantiation) remembers which devices have it.  Returns true the first time it is called for the current device.
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  const unsigned long long bit = 1ull << dev;
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
 
 // tmap.cu: TMA descriptors (SWIZZLE_128B, zero OOB fill)
 int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int rank, const uint64_t* dims,

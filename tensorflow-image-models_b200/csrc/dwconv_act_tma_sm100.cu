@@ -149,10 +149,9 @@ int launch_dw_tma(const void* x, const float* wgt, const float* bias, void* out,
   int rc = make_tmap(&tmap, x, kBF16, 4, dims, strides, box, "dwconv input", /*swizzle_bytes=*/0);
   if (rc != kOk) return rc;
   auto kernel = dwconv_act_tma_kernel<KS, STRIDE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   const int tiles_x = (Wo + Cfg::TW - 1) / Cfg::TW, tiles_y = (Ho + Cfg::TH - 1) / Cfg::TH;
   const int cslabs = (C + kSlab - 1) / kSlab;

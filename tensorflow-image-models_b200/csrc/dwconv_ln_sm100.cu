@@ -256,12 +256,11 @@ int launch_cluster(const void* x, const float* wgt, const float* bias, const flo
   using Cfg = DwCfg<CS>;
   auto kernel = dwconv7_ln_cluster_kernel<CS>;
   const int cl = C / CS;
-  static bool attr_set = false;
+  static unsigned long long attr_devs = 0;
   static int max_clusters[17] = {0};
-  if (!attr_set) {
+  if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
   }
   const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
   const long n_tiles = (long)B * tiles_x * tiles_y;

@@ -232,10 +232,9 @@ int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const void*
     tr = tc;
   }
   auto kernel = gemm_bf16_tcgen05_pair_kernel<OutT>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per instantiation
+  if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   const int tiles = ((M + kPairM - 1) / kPairM) * ((N + kBlockN - 1) / kBlockN);
   const int max_pairs = sm_count() / 2;

@@ -246,10 +246,9 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, const void* resi
     tr = tc;
   }
   auto kernel = gemm_bf16_tcgen05_kernel<BLOCK_N, OutT>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per instantiation
+  if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -292,10 +291,9 @@ int launch_conv(const void* x, const void* W, int ldw, const void* residual, voi
     }
   }
   auto kernel = gemm_bf16_tcgen05_kernel<BLOCK_N, OutT>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per instantiation
+  if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   const int tiles = (p.M / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();

@@ -208,10 +208,9 @@ int window_attention_bf16(const void* qkv, void* out, const float* bias, const i
   const long pairs = (long)B * nw_img * H;
   const unsigned grid = (unsigned)((pairs + kWWarps - 1) / kWWarps);
   constexpr int smem = kWWarps * 3 * kTileBytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(window_attention_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   window_attention_bf16_kernel<<<grid, kWWarps * 32, smem, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), bias, row_map, labels,

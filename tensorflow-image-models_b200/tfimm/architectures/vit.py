@@ -230,7 +230,12 @@ class ViT(Model):
                     hid = ops.gemm(hi, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)
                     ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], residual=xi, out=xi)
                 continue
-            a = ops.attention(qkv, B, T, Hh, dh, scale)
+            if qkv.dtype == torch.bfloat16 and not ops.attention_bf16_supported(T, dh):
+                # head_dim != 64 (vit_huge: 80) or K/V too long for shared memory: fp32 SIMT attention on the
+                # same bf16 qkv values (as Swin does for window-12 models); correctness first, not a fast path
+                a = ops.cast(ops.attention(ops.cast(qkv, torch.float32), B, T, Hh, dh, scale), torch.bfloat16)
+            else:
+                a = ops.attention(qkv, B, T, Hh, dh, scale)
             ops.gemm(a, blk["proj_w"], bias=blk["proj_b"], residual=xs, out=xs)
             h = ops.layernorm(xs, *blk["n2"], eps, adt)
             hid = ops.gemm(h, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)

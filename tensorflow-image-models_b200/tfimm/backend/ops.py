@@ -27,16 +27,30 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+# Device of the tensors of the launch being prepared (set by _cuda, read by _stream / _call): kernels run on the
+# device their operands live on and on THAT device's current stream, whatever torch's current device is.
+_dev = None
+
+
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(_dev).cuda_stream
 
 
 def _cuda(*tensors):
+    global _dev
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.KernelLibraryError(
                 "tfimm_b200 kernels only run on CUDA tensors (there is no CPU fallback)."
             )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _lib.KernelLibraryError(f"tfimm_b200: operands on different devices ({dev} and {t.device}).")
+    _dev = dev
 
 
 # When set to a list, every launch is bracketed by CUDA events on the launching stream and
@@ -47,6 +61,9 @@ trace = None
 def _call(name, *args, flops=0.0, nbytes=0.0):
     global launch_count
     fn = getattr(_lib.load(), name)
+    if _dev is not None and _dev.index is not None and _dev.index != torch.cuda.current_device():
+        with torch.cuda.device(_dev):  # cudaFuncSetAttribute / launches / SM count all refer to the current device
+            return _call(name, *args, flops=flops, nbytes=nbytes)
     if trace is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -185,6 +202,11 @@ def attention(qkv, B, N, H, dh, scale, bias=None, mask=None, probs=None, row_map
     else:
         raise _lib.KernelLibraryError("attention: unsupported dtype / option combination")
     return out
+
+
+def attention_bf16_supported(N, dh) -> bool:
+    """Shapes the bf16 tensor-core attention kernels take (csrc/attention.cu: head_dim 64, resident K/V <= 227 KB)."""
+    return dh == 64 and N <= 832
 
 
 def patchify(img, p, out_dtype, mean=None, inv_std=None, scale=1.0):

@@ -105,6 +105,7 @@ class Model:
         self.params: "OrderedDict[str, torch.Tensor]" = OrderedDict()
         self._specs = None
         self._plan = None  # engine-layout tensors derived from params (see _compile)
+        self._plan_version = 0  # bumped whenever the weights / device change (captured CUDA graphs check it)
         self._seed = seed
         self._build()
 
@@ -125,6 +126,7 @@ class Model:
             else:
                 self.params[key] = _init_tensor(spec, gen).to(self.device)
         self._plan = None
+        self._plan_version += 1
 
     @property
     def weights(self) -> List[Weight]:
@@ -163,12 +165,14 @@ class Model:
             if missing or unknown:
                 raise AttributeError(f"load_weights_dict: missing={missing[:5]} unknown={unknown[:5]}")
         self._plan = None
+        self._plan_version += 1
 
     def to(self, device):
         self.device = torch.device(device)
         for k in self.params:
             self.params[k] = self.params[k].to(self.device)
         self._plan = None
+        self._plan_version += 1
         return self
 
     # ------------------------------------------------------------------ engine helpers
@@ -286,7 +290,17 @@ class Model:
             static_out = self(static_in)
         launches = ops.launch_count - before
 
+        version = self._plan_version
+
         def run(x):
+            if x.dtype != static_in.dtype or tuple(x.shape) != tuple(static_in.shape):
+                # copy_ would silently CAST: uint8 pixels replayed through a float capture skip the fused
+                # (x/255 - mean)/std of the eager uint8 path.  Capture with dtype=torch.uint8 for raw pixels.
+                raise TypeError(f"cuda_graph captured for {tuple(static_in.shape)} {static_in.dtype}, "
+                                f"got {tuple(x.shape)} {x.dtype}")
+            if self._plan_version != version:
+                raise RuntimeError("the model's weights / device changed after cuda_graph() captured them; "
+                                   "capture a new graph")
             static_in.copy_(x, non_blocking=True)
             graph.replay()
             ops.launch_count += launches

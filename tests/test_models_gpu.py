@@ -336,3 +336,60 @@ def test_inference_pipeline_matches_direct_calls():
         outs.append(o.clone())
     for xb, o in zip(batches, outs):
         assert torch.equal(model(xb.cuda()).cpu(), o)
+
+
+@pytest.mark.parametrize("name,overrides", [
+    ("vit_huge_patch14_224_in21k", {"nb_blocks": 2}),          # head_dim 80: no bf16 tensor-core attention kernel
+    ("vit_base_patch8_224", {"nb_blocks": 2}),                 # 785 tokens: resident-K/V kernel with 128-row tiles
+    ("vit_base_patch16_384", {"nb_blocks": 2}),                # 577 tokens
+    ("vit_base_patch8_224", {"nb_blocks": 1, "input_size": (256, 256)}),   # 1025 tokens: fp32 attention fallback
+])
+def test_vit_shapes_outside_the_tcgen05_attention_kernel_run_in_bf16(name, overrides):
+    """Every registered ViT shape must run at the default precision: shapes the bf16 attention kernels
+    do not take fall back to the fp32 SIMT attention on the same bf16 qkv values."""
+    _, _, _, out, ref = _run(name, "vit", "bf16", 1, overrides)
+    rel, ab = _nerr(out, ref)
+    print(f"{name} {overrides} bf16: normalised {rel:.3e}")
+    assert rel < BF16_TOL
+
+
+def test_cuda_graph_rejects_wrong_dtype_and_stale_weights():
+    import tfimm
+    from oracle import params
+    from oracle import vit as ovit
+
+    model = tfimm.create_model("vit_tiny_patch16_224", precision="bf16", device="cuda", nb_blocks=1)
+    w = params.random_params(ovit.param_shapes(model.cfg), seed=9)
+    model.load_weights_dict(w)
+    fwd = model.cuda_graph(2)
+    x = params.test_images(2, 224, 224).cuda()
+    fwd(x)
+    with pytest.raises(TypeError):
+        fwd((x * 255).to(torch.uint8))          # a float capture must not silently cast raw pixels
+    with pytest.raises(TypeError):
+        fwd(x[:1])
+    fwd8 = model.cuda_graph(2, dtype=torch.uint8)   # raw pixels: capture with the fused preprocessing
+    raw = (x * 255).to(torch.uint8)
+    assert torch.equal(fwd8(raw), model(raw))
+    model.load_weights_dict(w)
+    with pytest.raises(RuntimeError):
+        fwd(x)                                   # weights changed after capture
+
+
+def test_model_on_second_device_if_present():
+    """Launches follow the tensors' device, not torch's current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import tfimm
+    from oracle import params
+    from oracle import vit as ovit
+
+    m0 = tfimm.create_model("vit_tiny_patch16_224", precision="bf16", device="cuda:0", nb_blocks=2)
+    m1 = tfimm.create_model("vit_tiny_patch16_224", precision="bf16", device="cuda:1", nb_blocks=2)
+    w = params.random_params(ovit.param_shapes(m0.cfg), seed=9)
+    m0.load_weights_dict(w)
+    m1.load_weights_dict(w)
+    x = params.test_images(2, 224, 224)
+    a = m0(x.to("cuda:0")).cpu()
+    b = m1(x.to("cuda:1")).cpu()          # current device is still cuda:0
+    assert torch.equal(a, b)
