@@ -27,6 +27,10 @@ from contextlib import contextmanager
 import torch
 import torch.nn.functional as F
 
+# Arithmetic precision of the emulation: float64, so that "exact per-op arithmetic" is not a figure of speech (cuDNN's
+# fp32 convolution algorithms -- Winograd / FFT -- are themselves only ~1e-5 accurate).
+_HP = torch.float64
+
 ACT_NAMES = (None, "", "linear", "none", "gelu", "swish", "silu", "relu", "relu6", "tanh", "sigmoid")
 
 
@@ -64,20 +68,20 @@ def _store(y, out, dtype):
 
 def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dtype=None, block_n=0,
          act_after_residual=False):
-    y = a.float() @ w.float().t()
+    y = a.to(_HP) @ w.to(_HP).t()
     if bias is not None:
-        y = y + bias.float()
-    r = residual.float() if residual is not None else None
+        y = y + bias.to(_HP)
+    r = residual.to(_HP) if residual is not None else None
     if act_after_residual:
         if gamma is not None:
-            y = y * gamma.float()
+            y = y * gamma.to(_HP)
         if r is not None:
             y = y + r
         y = _act(y, act)
     else:
         y = _act(y, act)
         if gamma is not None:
-            y = y * gamma.float()
+            y = y * gamma.to(_HP)
         if r is not None:
             y = y + r
     dt = out_dtype or (residual.dtype if residual is not None else a.dtype)
@@ -88,26 +92,26 @@ def conv_gemm(x, w, bias=None, ks=3, stride=1, pad=1, act=None, residual=None, a
               out_dtype=None):
     B, H, W, C = x.shape
     N = w.shape[0]
-    wt = w.float().view(N, ks, ks, C).permute(0, 3, 1, 2)
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    wt = w.to(_HP).view(N, ks, ks, C).permute(0, 3, 1, 2)
+    y = F.conv2d(x.to(_HP).permute(0, 3, 1, 2), wt, None, stride=stride, padding=pad).permute(0, 2, 3, 1)
     if bias is not None:
-        y = y + bias.float()
+        y = y + bias.to(_HP)
     if act_after_residual:
         if residual is not None:
-            y = y + residual.float()
+            y = y + residual.to(_HP)
         y = _act(y, act)
     else:
         y = _act(y, act)
         if residual is not None:
-            y = y + residual.float()
+            y = y + residual.to(_HP)
     return y.contiguous().to(out_dtype or (residual.dtype if residual is not None else x.dtype))
 
 
 def _ln(x, gamma, beta, eps):
-    x = x.float()
+    x = x.to(_HP)
     mean = x.mean(dim=-1, keepdim=True)
     var = (x - mean).pow(2).mean(dim=-1, keepdim=True)
-    return (x - mean) * torch.rsqrt(var + eps) * gamma.float() + beta.float()
+    return (x - mean) * torch.rsqrt(var + eps) * gamma.to(_HP) + beta.to(_HP)
 
 
 def layernorm(x, gamma, beta, eps, out_dtype, out=None):
@@ -133,13 +137,13 @@ def _softmax_pv(s, v, round_p):
     p = torch.exp(s - m)
     l = p.sum(dim=-1, keepdim=True)
     if round_p:
-        p = p.to(torch.bfloat16).float()
+        p = p.to(torch.bfloat16).to(_HP)
     return (p @ v) / l, p / l
 
 
 def attention(qkv, B, N, H, dh, scale, bias=None, mask=None, probs=None, row_map=None, nw_img=0):
     dt = qkv.dtype
-    x = qkv.float()
+    x = qkv.to(_HP)
     if row_map is not None:  # Swin: rows of window w of image b live at row_map[w*N + i] of that image's tokens
         nimg = B // nw_img
         tok = nw_img * N
@@ -148,10 +152,10 @@ def attention(qkv, B, N, H, dh, scale, bias=None, mask=None, probs=None, row_map
     q, k, v = x.view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
     s = scale * (q @ k.transpose(-1, -2))
     if bias is not None:
-        s = s + bias.float()[None]
+        s = s + bias.to(_HP)[None]
     if mask is not None:
         nm = mask.shape[0]
-        s = (s.view(B // nm, nm, H, N, N) + mask.float()[None, :, None]).view(B, H, N, N)
+        s = (s.view(B // nm, nm, H, N, N) + mask.to(_HP)[None, :, None]).view(B, H, N, N)
     o, p = _softmax_pv(s, v, round_p=(dt == torch.bfloat16))
     if probs is not None:
         probs.copy_(p)
@@ -164,7 +168,7 @@ def attention(qkv, B, N, H, dh, scale, bias=None, mask=None, probs=None, row_map
 
 
 def attention_cls(qkv, B, T, H, dh, scale, nq=1):
-    q, k, v = qkv.float().view(B, T, 3, H, dh).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.to(_HP).view(B, T, 3, H, dh).permute(2, 0, 3, 1, 4)
     s = scale * (q[:, :, :nq] @ k.transpose(-1, -2))
     o = torch.softmax(s, dim=-1) @ v  # SIMT kernel: fp32 throughout, one bf16 output rounding
     return o.permute(0, 2, 1, 3).reshape(B * nq, H * dh).contiguous().to(qkv.dtype)
@@ -174,15 +178,15 @@ def window_attention(qkv, bias, row_map, labels, B, nw_img, N, H, dh, scale):
     mask = None
     if labels is not None:
         lab = labels.view(nw_img, N)
-        mask = torch.where(lab[:, None, :] != lab[:, :, None], -100.0, 0.0).float()
+        mask = torch.where(lab[:, None, :] != lab[:, :, None], -100.0, 0.0).to(_HP)
     return attention(qkv, B * nw_img, N, H, dh, scale, bias=bias, mask=mask, row_map=row_map, nw_img=nw_img)
 
 
 def patchify(img, p, out_dtype, mean=None, inv_std=None, scale=1.0):
     B, H, W, C = img.shape
-    x = img.float()
+    x = img.to(_HP)
     if mean is not None:
-        x = (x * scale - mean.float()) * inv_std.float()
+        x = (x * scale - mean.to(_HP)) * inv_std.to(_HP)
     K = p * p * C
     y = x.view(B, H // p, p, W // p, p, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, K)
     Kpad = (K + 7) // 8 * 8
@@ -193,10 +197,10 @@ def patchify(img, p, out_dtype, mean=None, inv_std=None, scale=1.0):
 
 def assemble_tokens(patches, cls, dist, pos, B, P, out_dtype):
     D = patches.shape[1]
-    toks = [cls.float().view(1, 1, D).expand(B, 1, D)]
+    toks = [cls.to(_HP).view(1, 1, D).expand(B, 1, D)]
     if dist is not None:
-        toks.append(dist.float().view(1, 1, D).expand(B, 1, D))
-    y = torch.cat(toks + [patches.float().view(B, P, D)], dim=1) + pos.float()[None]
+        toks.append(dist.to(_HP).view(1, 1, D).expand(B, 1, D))
+    y = torch.cat(toks + [patches.to(_HP).view(B, P, D)], dim=1) + pos.to(_HP)[None]
     return y.reshape(-1, D).contiguous().to(out_dtype)
 
 
@@ -206,9 +210,9 @@ def cast(x, dtype):
 
 def _dw(x, wgt, bias, ks, stride, pads):
     C = x.shape[-1]
-    wt = wgt.float().view(ks, ks, C).permute(2, 0, 1)[:, None]
-    xin = F.pad(x.float().permute(0, 3, 1, 2), pads)
-    return F.conv2d(xin, wt, bias.float() if bias is not None else None, stride=stride, groups=C).permute(0, 2, 3, 1)
+    wt = wgt.to(_HP).view(ks, ks, C).permute(2, 0, 1)[:, None]
+    xin = F.pad(x.to(_HP).permute(0, 3, 1, 2), pads)
+    return F.conv2d(xin, wt, bias.to(_HP) if bias is not None else None, stride=stride, groups=C).permute(0, 2, 3, 1)
 
 
 def dwconv_ln(x, wgt, bias, gamma, beta, eps, out_dtype):
@@ -248,21 +252,21 @@ def _pads(H, W, ks, stride, padding):
 def dwconv_bias_act(x, wgt, bias, ks, stride, padding, act=None, pool_sum=None):
     B, H, W, C = x.shape
     _, _, pads = _pads(H, W, ks, stride, padding)
-    y = _act(_dw(x, wgt, bias, ks, stride, pads), act)
+    y = _act(_dw(x, wgt, bias, ks, stride, pads), act).contiguous().to(x.dtype)
     if pool_sum is not None:
-        pool_sum.add_(y.sum(dim=(1, 2)))
-    return y.contiguous().to(x.dtype)
+        pool_sum.add_(y.to(_HP).sum(dim=(1, 2)).to(pool_sum.dtype))  # the squeeze sees what the next layer reads
+    return y
 
 
 def global_avg_pool(x):
     B, C = x.shape[0], x.shape[-1]
-    return x.float().reshape(B, -1, C).mean(dim=1)
+    return x.to(_HP).reshape(B, -1, C).mean(dim=1)
 
 
 def im2col(x, ks, stride, padding, out_dtype, groups=1):
     B, H, W, C = x.shape
     Ho, Wo, pads = _pads(H, W, ks, stride, padding)
-    xin = F.pad(x.float().permute(0, 3, 1, 2), pads)
+    xin = F.pad(x.to(_HP).permute(0, 3, 1, 2), pads)
     cols = F.unfold(xin, ks, stride=stride)  # (B, C*ks*ks, L), rows ordered (c, ky, kx)
     cols = cols.view(B, C, ks * ks, Ho * Wo).permute(0, 3, 2, 1)  # (B, L, (ky,kx), c)
     cg = C // groups
@@ -278,29 +282,29 @@ def im2col(x, ks, stride, padding, out_dtype, groups=1):
 
 
 def group_norm(x, gamma, beta, groups, eps, act=None, residual=None):
-    y = F.group_norm(x.float().permute(0, 3, 1, 2), groups, gamma.float(), beta.float(), eps).permute(0, 2, 3, 1)
+    y = F.group_norm(x.to(_HP).permute(0, 3, 1, 2), groups, gamma.to(_HP), beta.to(_HP), eps).permute(0, 2, 3, 1)
     if residual is not None:
-        y = y + residual.float()
+        y = y + residual.to(_HP)
     return _act(y, act).contiguous().to(x.dtype)
 
 
 def blur_pool(x, stride=2):
     C = x.shape[-1]
-    xc = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect")
-    k1 = torch.tensor([1.0, 2.0, 1.0], device=x.device)
+    xc = F.pad(x.to(_HP).permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect")
+    k1 = torch.tensor([1.0, 2.0, 1.0], device=x.device, dtype=_HP)
     k = (k1[:, None] * k1[None, :] / 16)[None, None].repeat(C, 1, 1, 1)
     return F.conv2d(xc, k, stride=stride, groups=C).permute(0, 2, 3, 1).contiguous().to(x.dtype)
 
 
 def se_gate(pooled_sum, hw, w_reduce, b_reduce, w_expand, b_expand, act, gate_act="sigmoid"):
-    m = pooled_sum.float() / float(hw)
-    h = _act(m @ w_reduce.float().t() + b_reduce.float(), act)
-    return _act(h @ w_expand.float() + b_expand.float(), gate_act)
+    m = pooled_sum.to(_HP) / float(hw)
+    h = _act(m @ w_reduce.to(_HP).t() + b_reduce.to(_HP), act)
+    return _act(h @ w_expand.to(_HP) + b_expand.to(_HP), gate_act)
 
 
 def scale_channels_(x, gate):
     B, C = gate.shape
-    y = x.float().view(B, -1, C) * gate.float()[:, None, :]
+    y = x.to(_HP).view(B, -1, C) * gate.to(_HP)[:, None, :]
     x.copy_(y.view(x.shape).to(x.dtype))
     return x
 
@@ -308,7 +312,7 @@ def scale_channels_(x, gate):
 def pool2d(x, ks, stride, padding, mode):
     B, H, W, C = x.shape
     _, _, pads = _pads(H, W, ks, stride, padding)
-    xin = x.float().permute(0, 3, 1, 2)
+    xin = x.to(_HP).permute(0, 3, 1, 2)
     if mode == "avg":
         num = F.avg_pool2d(F.pad(xin, pads), ks, stride, divisor_override=1)
         cnt = F.avg_pool2d(F.pad(torch.ones_like(xin[:, :1]), pads), ks, stride, divisor_override=1)
@@ -322,21 +326,21 @@ def pool2d(x, ks, stride, padding, mode):
 
 def grouped_conv(x, wgt, bias, cg, ks, stride, pad, act=None):
     C = x.shape[-1]
-    w = wgt.float().view(ks, ks, cg, C).permute(3, 2, 0, 1)
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, bias.float() if bias is not None else None, stride=stride,
+    w = wgt.to(_HP).view(ks, ks, cg, C).permute(3, 2, 0, 1)
+    y = F.conv2d(x.to(_HP).permute(0, 3, 1, 2), w, bias.to(_HP) if bias is not None else None, stride=stride,
                  padding=pad, groups=C // cg).permute(0, 2, 3, 1)
     return _act(y, act).contiguous().to(x.dtype)
 
 
 def eca_gate(mean, w):
     k = w.numel()
-    y = F.conv1d(F.pad(mean.float(), (k // 2, k // 2))[:, None], w.float()[None, None])[:, 0]
+    y = F.conv1d(F.pad(mean.to(_HP), (k // 2, k // 2))[:, None], w.to(_HP)[None, None])[:, 0]
     return torch.sigmoid(y)
 
 
 def scale_add_act_(x, gate, shortcut, act):
     B, C = gate.shape
-    y = x.float().view(B, -1, C) * gate.float()[:, None, :] + shortcut.float().view(B, -1, C)
+    y = x.to(_HP).view(B, -1, C) * gate.to(_HP)[:, None, :] + shortcut.to(_HP).view(B, -1, C)
     x.copy_(_act(y, act).view(x.shape).to(x.dtype))
     return x
 

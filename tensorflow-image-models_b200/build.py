@@ -40,7 +40,11 @@ def _digest(paths):
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, defines=(), out: Path = None) -> Path:
+    """defines / out: build a variant of the library (e.g. -DTFIMM_FAST_ACT for an A/B measurement) into another
+    file; load it with TFIMM_B200_LIB=<path>.  The default build is the product."""
+    if defines or out is not None:
+        return _build_variant(list(defines), Path(out or (OBJ_DIR / "libtfimm_b200_variant.so")))
     sources = sorted(CSRC.glob("*.cu"))
     headers = sorted(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "tfimm_b200.h"]
     stamp = OBJ_DIR / "stamp.txt"
@@ -77,9 +81,34 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def _build_variant(defines, out: Path) -> Path:
+    obj_dir = OBJ_DIR / ("variant_" + hashlib.sha256(" ".join(defines).encode()).hexdigest()[:8])
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    flags = NVCC_FLAGS + [f"-D{d}" for d in defines]
+
+    def compile_one(src: Path):
+        obj = obj_dir / (src.stem + ".o")
+        return obj, subprocess.run([NVCC, *flags, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        results = list(pool.map(compile_one, sorted(CSRC.glob("*.cu"))))
+    for obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stderr)
+            raise RuntimeError(f"nvcc failed on {obj.stem}")
+    res = subprocess.run([NVCC, "-shared", "-o", str(out), *[str(o) for o, _ in results],
+                          "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("link failed")
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--define", action="append", default=[], help="extra -D macro: builds a VARIANT library")
+    ap.add_argument("--out", default=None, help="output path of the variant library")
     args = ap.parse_args()
-    print(build(force=args.force, verbose=args.verbose))
+    print(build(force=args.force, verbose=args.verbose, defines=args.define, out=args.out))

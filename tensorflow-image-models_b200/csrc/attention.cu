@@ -268,7 +268,6 @@ __global__ void attention_f32_kernel(const float* __restrict__ qkv, float* __res
 
 }  // namespace
 
-int attention_bf16_tc(const void* qkv, void* out, int B, int N, int H, float scale, cudaStream_t stream);
 int attention_bf16_tc2(const void* qkv, void* out, int B, int N, int H, float scale, cudaStream_t stream);
 
 int attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, float scale,
@@ -280,17 +279,9 @@ int attention_bf16(const void* qkv, void* out, int B, int N, int H, int dh, floa
   }
   TFIMM_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
                   "attention: pointers must be 16-byte aligned");
-  // Short sequences (ViT-B/16 @224: N = 197) run on tcgen05; longer ones on the resident-KV mma.sync
-  // kernel.  TFIMM_B200_ATTN=mma forces the latter (debugging aid).
-  // TFIMM_B200_ATTN = "mma" (legacy mma.sync) | "tc1" (one CTA per 128-query tile) | default: persistent tc2.
-  static const int mode = [] {
-    const char* e = getenv("TFIMM_B200_ATTN");
-    if (e == nullptr) return 2;
-    if (e[0] == 'm') return 0;
-    return (e[0] == 't' && e[1] == 'c' && e[2] == '1') ? 1 : 2;
-  }();
-  if (N <= 256 && mode == 2) return attention_bf16_tc2(qkv, out, B, N, H, scale, stream);
-  if (N <= 256 && mode == 1) return attention_bf16_tc(qkv, out, B, N, H, scale, stream);
+  // Short sequences (ViT-B/16 @224: N = 197) run on tcgen05 (attention_sm100.cu); longer ones on the resident-KV
+  // mma.sync kernel below.
+  if (N <= 256) return attention_bf16_tc2(qkv, out, B, N, H, scale, stream);
   auto q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   auto o = reinterpret_cast<__nv_bfloat16*>(out);
   // resident K/V + one query tile per CTA must fit 227 KB: 224-row tiles up to N = 784, 128-row tiles up to N = 832

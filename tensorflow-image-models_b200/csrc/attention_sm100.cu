@@ -1,11 +1,8 @@
 // tcgen05 self-attention for short sequences (N <= 256 keys, head_dim 64): the ViT-B/16 case
-// (N = 197) of tfimm/architectures/vit.py:149-165.
-//
-// One CTA = one (image, head, 128-query tile); two CTAs are resident per SM so one CTA's loads /
-// softmax overlap the other's MMAs.
+// (N = 197) of tfimm/architectures/vit.py:149-165.  Persistent, warp-specialised, one CTA per SM.
 //   TMA (3D maps over the packed qkv projection, zero-fill past the sequence end)
-//        Q tile [128 x 64], K [npad x 64], V [npad x 64] -> 128B-swizzled smem
-//   S = Q K^T        one tcgen05.mma chain (M=128, N=npad, K=64), fp32 scores in TMEM cols [0, npad)
+//        Q [256 x 64], K [npad x 64], V [npad x 64] of work item i+1 -> 128B-swizzled smem while item i runs
+//   S = Q K^T        one tcgen05.mma chain per 128-query tile (M=128, N=npad, K=64), fp32 scores in TMEM
 //   softmax          each thread owns one query row: tcgen05.ld, max, exp2, row sum in registers;
 //                    P (bf16) is written back over the consumed score columns (TMEM cols [0, npad/2))
 //   O = P V          tcgen05.mma with A = P from TMEM and B = V from smem as an MN-major operand
@@ -20,201 +17,89 @@ namespace {
 constexpr int kDH = 64;
 constexpr int kQRows = 128;
 constexpr int kMaxKeys = 256;
-constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kOCol = 128;
-
-constexpr int kQBytes = kQRows * 128;          // 16 KB
 constexpr int kKVBytesMax = kMaxKeys * 128;    // 32 KB each
-constexpr int kSmemBytes = kQBytes + 2 * kKVBytesMax + 64 + 1024;
 
-__global__ void __launch_bounds__(128, 2)
-vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                        const __grid_constant__ CUtensorMap tmap_o, int N, int H, float scale_log2) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t sQ = smem_base;
-  const uint32_t sK = sQ + kQBytes;
-  const uint32_t sV = sK + kKVBytesMax;
-  const uint32_t bar_load = sV + kKVBytesMax;
-  const uint32_t bar_s = bar_load + 8;
-  const uint32_t bar_o = bar_load + 16;
-  const uint32_t tmem_ptr_smem = bar_load + 24;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kQRows, h = blockIdx.y, b = blockIdx.z;
-  const int D = H * kDH;
-  const int npad = (N + 15) & ~15;
-
-  if (threadIdx.x == 0) {
-    prefetch_tmap(&tmap_q);
-    prefetch_tmap(&tmap_kv);
-    prefetch_tmap(&tmap_o);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
-    fence_mbar_init();
+// Row softmax of one 128-query tile, thread = query row, for a COMPILE-TIME key count (NFULL 32-column chunks plus
+// an optional 16-column tail): scores S (fp32, TMEM columns [0, npad) of this warp's lane quarter at t_row) ->
+// P = exp2((S - max) * scale_log2) as packed bf16 in columns [0, npad/2); returns the fp32 row sum of the unrounded
+// P.  Two passes over TMEM (max, then exp), each fully unrolled with the load of chunk c+1 in flight while chunk c
+// is processed in the OTHER register buffer (no copies); only the last chunk is masked against the true key count N
+// (its padding columns hold 0 = q . 0, which must neither win the max nor enter the sum).
+// Instruction budget per row of 208 keys: 14 LDTM + 104 FMNMX3 + 104 FFMA2 + 208 MUFU.EX2 + 104 FADD2 + 104 F2FP +
+// 13 STTM: the MUFU pipe (16 lanes / clk / SM) is the floor.
+template <int NFULL, bool TAIL16>
+__device__ __forceinline__ float softmax_tile_unrolled(uint32_t t_row, int N, float scale_log2) {
+  constexpr int NCH = NFULL + (TAIL16 ? 1 : 0);
+  uint32_t buf[2][32];
+  auto issue = [&](int c, uint32_t (&rg)[32]) {
+    if (!TAIL16 || c < NFULL) {
+      tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), rg);
+    } else {
+      uint32_t r16[16];
+      tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 32), r16);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) rg[j] = r16[j];
+    }
+  };
+  // ---- pass 1: row maximum ----
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  issue(0, buf[0]);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    tmem_ld_wait();
+    if (c + 1 < NCH) issue(c + 1, buf[(c + 1) & 1]);
+    const uint32_t (&v)[32] = buf[c & 1];
+    const int width = (TAIL16 && c == NFULL) ? 16 : 32;
+    if (c + 1 < NCH) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2)
+        mx[(j >> 1) & 3] = fmaxf(mx[(j >> 1) & 3], fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+    } else {
+#pragma unroll
+      for (int j = 0; j < width; ++j)
+        mx[j & 3] = fmaxf(mx[j & 3], (c * 32 + j < N) ? __uint_as_float(v[j]) : -INFINITY);
+    }
   }
-  if (warp == 0) tmem_alloc<kTmemCols>(tmem_ptr_smem);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
-
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar_load, (uint32_t)(kQBytes + 2 * npad * 128));
-    tma_load_3d(sQ, &tmap_q, bar_load, h * kDH, m0, b);
-    tma_load_3d(sK, &tmap_kv, bar_load, D + h * kDH, 0, b);
-    tma_load_3d(sV, &tmap_kv, bar_load, 2 * D + h * kDH, 0, b);
-    mbar_wait(bar_load, 0);
-    tcgen05_fence_after();
-    // S = Q K^T
-    const uint32_t idesc_s = umma_idesc_bf16_f32(kQRows, npad);
-    const uint64_t dq = umma_desc_k_sw128(sQ), dk = umma_desc_k_sw128(sK);
+  const float mx_all = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+  const uint64_t sl2 = splat2(scale_log2), nmoff = splat2(-mx_all * scale_log2);
+  // ---- pass 2: P = exp2(S * scale_log2 - max * scale_log2), row sum, bf16 P back into TMEM ----
+  uint64_t sum[4] = {splat2(0.f), splat2(0.f), splat2(0.f), splat2(0.f)};
+  issue(0, buf[0]);
 #pragma unroll
-    for (int k = 0; k < kDH / 16; ++k)
-      umma_bf16_ss(tmem_base, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
-    umma_commit(bar_s);
-  }
-  mbar_wait(bar_s, 0);
-  tcgen05_fence_after();
-
-  // ---- softmax: thread (warp, lane) owns query row m0 + 32*warp + lane (TMEM lane 32*warp + lane) ----
-  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const bool warp_has_rows = (m0 + warp * 32) < N;
-  float row_sum = 1.f;
-  if (warp_has_rows) {
-    // Scores are consumed in 32-column chunks (the last one may be 16 wide); the load of chunk c+1 is
-    // in flight while chunk c is processed.
-    const int nfull = npad >> 5;           // 32-wide chunks
-    const bool tail16 = (npad & 16) != 0;  // one extra 16-wide chunk
-    const int nchunks = nfull + (tail16 ? 1 : 0);
-    auto issue = [&](int c, uint32_t (&r)[32]) {
-      if (c < nfull) {
-        tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), r);
-      } else {
-        uint32_t t16[16];
-        tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 32), t16);
+  for (int c = 0; c < NCH; ++c) {
+    tmem_ld_wait();
+    if (c + 1 < NCH) issue(c + 1, buf[(c + 1) & 1]);
+    const uint32_t (&v)[32] = buf[c & 1];
+    const int width = (TAIL16 && c == NFULL) ? 16 : 32;
+    uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = t16[j];
-#pragma unroll
-        for (int j = 16; j < 32; ++j) r[j] = 0xff800000u;  // -inf
+    for (int j = 0; j < width / 2; ++j) {
+      float t0, t1;
+      unpack2(fma2(pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sl2, nmoff), t0, t1);
+      float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+      if (c + 1 == NCH) {
+        p0 = (c * 32 + 2 * j < N) ? p0 : 0.f;
+        p1 = (c * 32 + 2 * j + 1 < N) ? p1 : 0.f;
       }
-    };
-    float mx = -INFINITY;
-    {
-      uint32_t r[32], cur[32];
-      issue(0, r);
-      for (int c = 0; c < nchunks; ++c) {
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) cur[j] = r[j];
-        if (c + 1 < nchunks) issue(c + 1, r);
-        if (c * 32 + 32 <= N) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < N) mx = fmaxf(mx, __uint_as_float(cur[j]));
-        }
-      }
+      sum[j & 3] = add2(sum[j & 3], pack2(p0, p1));
+      pk[j] = pack_bf16x2(p0, p1);
     }
-    const float moff = mx * scale_log2;
-    const uint64_t sl2 = splat2(scale_log2), nmoff = splat2(-moff);
-    uint64_t sum2 = splat2(0.f);
-    {
-      uint32_t r[32], cur[32];
-      issue(0, r);
-      for (int c = 0; c < nchunks; ++c) {
-        tmem_ld_wait();
+    // P chunk c overwrites score columns [16c, 16c + width/2): consumed already (the load in flight is chunk c+1)
+    uint32_t lo[8], hi[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) cur[j] = r[j];
-        if (c + 1 < nchunks) issue(c + 1, r);
-        uint32_t pk[16];
-        const bool full = (c * 32 + 32 <= N);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float t0, t1;
-          unpack2(fma2(pack2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), sl2, nmoff), t0, t1);
-          float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
-          if (!full) {
-            p0 = (c * 32 + 2 * j < N) ? p0 : 0.f;
-            p1 = (c * 32 + 2 * j + 1 < N) ? p1 : 0.f;
-          }
-          sum2 = add2(sum2, pack2(p0, p1));
-          pk[j] = pack_bf16x2(p0, p1);
-        }
-        // P chunk c overwrites score columns [16c, 16c+16): all already consumed (<= chunk c)
-        uint32_t lo[8], hi[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { lo[j] = pk[j]; hi[j] = pk[8 + j]; }
-        tmem_st_32x32b_x8(t_row + (uint32_t)(c * 16), lo);
-        if (c < nfull) tmem_st_32x32b_x8(t_row + (uint32_t)(c * 16 + 8), hi);
-      }
-    }
-    {
-      float s0, s1;
-      unpack2(sum2, s0, s1);
-      row_sum = s0 + s1;
-    }
-    tmem_st_wait();
+    for (int j = 0; j < 8; ++j) { lo[j] = pk[j]; hi[j] = (width == 32) ? pk[8 + j] : 0u; }
+    tmem_st_32x32b_x8(t_row + (uint32_t)(c * 16), lo);
+    if (width == 32) tmem_st_32x32b_x8(t_row + (uint32_t)(c * 16 + 8), hi);
   }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-
-  if (threadIdx.x == 0) {
-    // O = P V : A = P (TMEM, 8 packed columns per 16 keys), B = V (smem, MN-major, 16 keys = 2048 B)
-    const uint32_t idesc_o = umma_idesc_bf16_f32(kQRows, kDH, /*b_mn_major=*/true);
-    const int ksteps = npad >> 4;
-    for (int j = 0; j < ksteps; ++j) {
-      const uint64_t dv = umma_desc_mn_sw128(sV + (uint32_t)(j * 2048), (uint32_t)(npad * 128));
-      umma_bf16_ts(tmem_base + kOCol, tmem_base + (uint32_t)(j * 8), dv, idesc_o, (uint32_t)(j != 0));
-    }
-    umma_commit(bar_o);
-  }
-  mbar_wait(bar_o, 0);
-  tcgen05_fence_after();
-
-  if (warp_has_rows) {
-    const float inv = 1.0f / row_sum;
-    uint8_t* my_row = smem_gen + (size_t)warp * 4096 + lane * 128;  // Q region is dead: reuse as store slab
-    const int sw = lane & 7;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(t_row + kOCol + (uint32_t)(c * 16), r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(r[8 * q + 0]) * inv, __uint_as_float(r[8 * q + 1]) * inv);
-        u.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv);
-        u.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv);
-        u.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv);
-        *reinterpret_cast<uint4*>(my_row + (((2 * c + q) ^ sw) << 4)) = u;
-      }
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_3d(&tmap_o, sQ + (uint32_t)warp * 4096u, h * kDH, m0 + warp * 32, b);
-      tma_store_commit();
-      tma_store_wait_read<0>();  // smem may be released; the global writes complete with the grid
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tcgen05_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
-  }
+  tmem_st_wait();
+  float s0, s1;
+  unpack2(add2(add2(sum[0], sum[1]), add2(sum[2], sum[3])), s0, s1);
+  return s0 + s1;
 }
 
-
 // ---------------------------------------------------------------------------------------------------
-// v2: persistent, warp-specialised, two-stage pipeline (one CTA per SM)
+// persistent, warp-specialised, two-stage pipeline (one CTA per SM)
 // ---------------------------------------------------------------------------------------------------
 //   warp 0      TMA producer: Q (256 rows), K, V of work item i+1 while item i is being processed
 //   warp 1      tcgen05.mma issuer: S = Q K^T for both 128-query tiles, later O = P V for both
@@ -356,7 +241,12 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         mbar_wait(sfull_bar(r), par);
         tcgen05_fence_after();
         float row_sum = 1.f;
-        if (warp_has_rows) {
+        if (warp_has_rows && npad == 208) {
+          row_sum = softmax_tile_unrolled<6, true>(t_row, N, scale_log2);   // ViT-B/16, DeiT @224: 197 / 198 tokens
+        } else if (warp_has_rows && npad == 64) {
+          row_sum = softmax_tile_unrolled<2, false>(t_row, N, scale_log2);  // patch-32 models @224: 50 tokens
+        } else if (warp_has_rows) {
+          // any other key count: run-time chunk loop
           // four independent running maxima / sums: one accumulator would be a 208-deep dependent chain per row
           float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
           {
@@ -420,16 +310,11 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 
         mbar_wait(ofull_bar(r), par);
         tcgen05_fence_after();
-        uint32_t o[64];
+        uint32_t o0[32], o1[32];
         if (warp_has_rows) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t t32[32];
-            tmem_ld_32x32b_x32(t_row + kOCol + (uint32_t)(c * 32), t32);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[c * 32 + j] = t32[j];
-          }
+          tmem_ld_32x32b_x32(t_row + kOCol, o0);
+          tmem_ld_32x32b_x32(t_row + kOCol + 32u, o1);
+          tmem_ld_wait();
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -441,11 +326,13 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           const int sw = lane & 7;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            const uint32_t (&o)[32] = j < 4 ? o0 : o1;
+            const int e = 8 * (j & 3);
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+            u.x = pack_bf16x2(__uint_as_float(o[e + 0]) * inv, __uint_as_float(o[e + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(o[e + 2]) * inv, __uint_as_float(o[e + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(o[e + 4]) * inv, __uint_as_float(o[e + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(o[e + 6]) * inv, __uint_as_float(o[e + 7]) * inv);
             *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = u;
           }
           fence_proxy_async_smem();
@@ -500,36 +387,6 @@ int attention_bf16_tc2(const void* qkv, void* out, int B, int N, int H, float sc
   vit_attention_tc2_kernel<<<grid, kP2Threads, kP2SmemBytes, stream>>>(tq, tkv, to, N, H, items,
                                                                        scale * 1.4426950408889634f);
   TFIMM_LAUNCH_OK("vit_attention_tc2_kernel");
-  return kOk;
-}
-
-int attention_bf16_tc(const void* qkv, void* out, int B, int N, int H, float scale, cudaStream_t stream) {
-  const int D = H * kDH;
-  const int npad = (N + 15) & ~15;
-  CUtensorMap tq, tkv, to;
-  {
-    const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)N, (uint64_t)B};
-    const uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)N * 3 * D * 2};
-    const uint32_t box_q[3] = {kDH, kQRows, 1};
-    const uint32_t box_kv[3] = {kDH, (uint32_t)npad, 1};
-    int st;
-    if ((st = make_tmap(&tq, qkv, kBF16, 3, dims, strides, box_q, "attention q")) != kOk) return st;
-    if ((st = make_tmap(&tkv, qkv, kBF16, 3, dims, strides, box_kv, "attention kv")) != kOk) return st;
-  }
-  {
-    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)N, (uint64_t)B};
-    const uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)N * D * 2};
-    const uint32_t box[3] = {kDH, 32, 1};
-    int st;
-    if ((st = make_tmap(&to, out, kBF16, 3, dims, strides, box, "attention out")) != kOk) return st;
-  }
-  static unsigned long long attr_devs = 0;
-  if (first_use_on_device(attr_devs)) {
-    TFIMM_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  }
-  dim3 grid((N + kQRows - 1) / kQRows, H, B);
-  vit_attention_tc_kernel<<<grid, 128, kSmemBytes, stream>>>(tq, tkv, to, N, H, scale * 1.4426950408889634f);
-  TFIMM_LAUNCH_OK("vit_attention_tc_kernel");
   return kOk;
 }
 

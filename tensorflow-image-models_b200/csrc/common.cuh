@@ -172,6 +172,58 @@ __device__ __forceinline__ uint64_t gelu_tanh2(uint64_t x) {
   return mul2(x, fma2(pack2(tanh_approx(g0), tanh_approx(g1)), splat2(0.5f), splat2(0.5f)));
 }
 
+// ---- accurate activations for the tensor-core epilogues (packed pairs, groups of FOUR elements) ----
+// The bf16 parity budget (tests/test_parity_budget_gpu.py) needs every value to be right to ~1e-5 BEFORE it is rounded
+// to bf16: a pre-rounding error d flips the rounding of a fraction d/ulp of the elements by a whole ulp, i.e. it adds
+// noise of variance d*ulp against the ulp^2/12 inherent to bf16 storage -- tanh.approx (2^-11) would DOUBLE the noise.
+// Both activations are written as x * sigma with sigma = 1 / (1 + 2^u):
+//   * 2^u is one MUFU.EX2 (rel. error 2^-22);
+//   * the division is shared by four elements: 1/(d0 d1 d2 d3) is ONE MUFU.RCP, the four quotients are recovered with
+//     nine multiplications (d <= 1 + 2^28, so the product stays below 2^127)
+// => 1.25 MUFU operations per element instead of 2 (MUFU: 16 lanes / clk / SM is the epilogue's narrowest pipe).
+__device__ __forceinline__ void sigma4_from_log2(uint64_t u01, uint64_t u23, uint64_t& s01, uint64_t& s23) {
+  float u0, u1, u2, u3;
+  unpack2(u01, u0, u1);
+  unpack2(u23, u2, u3);
+  const uint64_t one2 = splat2(1.0f);
+  float d0, d1, d2, d3;
+  unpack2(add2(pack2(ex2_approx(fminf(u0, 28.f)), ex2_approx(fminf(u1, 28.f))), one2), d0, d1);
+  unpack2(add2(pack2(ex2_approx(fminf(u2, 28.f)), ex2_approx(fminf(u3, 28.f))), one2), d2, d3);
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float inv = rcp_approx(p01 * p23);
+  const float r01 = inv * p23, r23 = inv * p01;  // 1 / (d0 d1), 1 / (d2 d3)
+  s01 = mul2(pack2(d1, d0), splat2(r01));        // (1/d0, 1/d1)
+  s23 = mul2(pack2(d3, d2), splat2(r23));
+}
+// swish(x) = x * sigmoid(x), sigmoid(x) = 1 / (1 + 2^(-x log2 e)).
+__device__ __forceinline__ void swish4(uint64_t& x01, uint64_t& x23) {
+  const uint64_t nl2e = splat2(-1.4426950408889634f);
+  uint64_t s01, s23;
+  sigma4_from_log2(mul2(x01, nl2e), mul2(x23, nl2e), s01, s23);
+  x01 = mul2(x01, s01);
+  x23 = mul2(x23, s23);
+}
+// erf-GELU: Phi(x) = 1 / (1 + 2^(-x q(x^2))) holds exactly for x q(x^2) ln 2 = logit(Phi(x)); q is a degree-4
+// polynomial in x^2 fitted on |x| <= 5.5 (x^2 is clamped there: beyond it Phi is 0 / 1 to 2e-8 and q keeps its edge
+// value, so u stays monotone).  Max |error| of x Phi(x) against the exact erf form, evaluated in fp32: 3.6e-6
+// (tools/fit_gelu.py), i.e. < 1/500 of a bf16 ulp for |y| >= 0.5.
+__device__ __forceinline__ uint64_t gelu_neg_log2_odds(uint64_t x) {
+  float x0, x1;
+  unpack2(mul2(x, x), x0, x1);
+  const uint64_t t = pack2(fminf(x0, 30.25f), fminf(x1, 30.25f));
+  uint64_t q = fma2(splat2(3.2899208690650994e-06f), t, splat2(-8.927415183279663e-05f));
+  q = fma2(q, t, splat2(-0.0003550456603989005f));
+  q = fma2(q, t, splat2(0.10521824657917023f));
+  q = fma2(q, t, splat2(2.3020482063293457f));
+  return mul2(mul2(x, splat2(-1.0f)), q);
+}
+__device__ __forceinline__ void gelu4(uint64_t& x01, uint64_t& x23) {
+  uint64_t s01, s23;
+  sigma4_from_log2(gelu_neg_log2_odds(x01), gelu_neg_log2_odds(x23), s01, s23);
+  x01 = mul2(x01, s01);
+  x23 = mul2(x23, s23);
+}
+
 template <bool kPrecise>
 __device__ __forceinline__ float gelu_erf(float x) {
   if constexpr (kPrecise) {

@@ -24,6 +24,9 @@ int dwconv_bias_act_pairs(const void* x, int dtype, const float* wgt, const floa
 int dwconv_bias_act_tma(const void* x, int dtype, const float* wgt, const float* bias, void* out, float* pool_sum,
                         int B, int H, int W, int C, int ks, int stride, int pad_t, int pad_l, int Ho, int Wo, int act,
                         cudaStream_t stream);
+int dwconv7_ln_tmem(const void* x, int in_dtype, const float* wgt, const float* bias, const float* gamma,
+                    const float* beta, void* out, int out_dtype, int B, int H, int W, int C, float eps,
+                    cudaStream_t stream);
 int dwconv7_ln_cluster(const void* x, int in_dtype, const float* wgt, const float* bias, const float* gamma,
                        const float* beta, void* out, int out_dtype, int B, int H, int W, int C, float eps,
                        cudaStream_t stream);
@@ -583,16 +586,12 @@ int dwconv_ln(const void* x, int in_dtype, const float* wgt, const float* bias, 
   TFIMM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "dwconv_ln: need C%%4==0 (C=%d)", C);
   TFIMM_CHECK_ARG(ks == 7, "dwconv_ln: only kernel size 7 is instantiated (got %d)", ks);
   {
-    // Fast path: channel-slab / cluster kernel (dwconv_ln_sm100.cu) whenever C splits into 1/2/4/8 slabs of
-    // 96 or 128 channels -- every registered ConvNeXt up to `base`.  TFIMM_B200_DWCONV=generic disables it.
-    static const bool force_generic = [] {
-      const char* e = getenv("TFIMM_B200_DWCONV");
-      return e != nullptr && e[0] == 'g';
-    }();
-    if (!force_generic) {
-      const int st = dwconv7_ln_cluster(x, in_dtype, wgt, bias, gamma, beta, out, out_dtype, B, H, W, C, eps, stream);
-      if (st != kUnsupported) return st;
-    }
+    // Fast paths (fp32 residual stream in, bf16 out): the tensor-memory kernel (dwconv_ln_tmem_sm100.cu) for C a
+    // multiple of 64, else the thread-block-cluster kernel (dwconv_ln_sm100.cu: 32-channel slabs, e.g. C = 96).
+    int st = dwconv7_ln_tmem(x, in_dtype, wgt, bias, gamma, beta, out, out_dtype, B, H, W, C, eps, stream);
+    if (st != kUnsupported) return st;
+    st = dwconv7_ln_cluster(x, in_dtype, wgt, bias, gamma, beta, out, out_dtype, B, H, W, C, eps, stream);
+    if (st != kUnsupported) return st;
   }
   constexpr int TW = 7;
   // warps per CTA limited by the [TW][C] fp32 stash per warp

@@ -39,15 +39,29 @@ struct RawPair<float> {
   static __device__ __forceinline__ uint64_t to_f32x2(type u) { return u; }
 };
 
-template <bool kFast>
-__device__ __forceinline__ uint64_t act_pair(uint64_t v, int act) {
-  if (kFast) {
-    if (act == kActSwish) return swish_fast2(v);
-    if (act == kActNone) return v;
+// Activation of a whole output strip.  bf16 mode: accurate swish on groups of four elements (common.cuh); fp32 mode
+// (the 1e-5 structural-parity path): libm-exact scalar forms.
+template <bool kBf16, int N>
+__device__ __forceinline__ void act_strip(uint64_t (&acc)[N], int act) {
+  if (act == kActNone) return;
+  if (kBf16 && act == kActSwish && N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+#ifdef TFIMM_FAST_ACT
+      acc[i] = swish_fast2(acc[i]);
+      acc[i + 1] = swish_fast2(acc[i + 1]);
+#else
+      swish4(acc[i], acc[i + 1]);
+#endif
+    }
+    return;
   }
-  float a, b;
-  unpack2(v, a, b);
-  return pack2(apply_act<!kFast>(a, act), apply_act<!kFast>(b, act));
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float a, b;
+    unpack2(acc[i], a, b);
+    acc[i] = pack2(apply_act<!kBf16>(a, act), apply_act<!kBf16>(b, act));
+  }
 }
 
 template <typename T, int KS, int STRIDE, int TW>
@@ -137,10 +151,11 @@ dwconv_act_pairs_kernel(const T* __restrict__ x, const float* __restrict__ wgt /
         }
       }
     }
+    act_strip<sizeof(T) == 2>(acc, act);
 #pragma unroll
     for (int i = 0; i < TW; ++i) {
       if (ox0 + i < Wo) {
-        const uint64_t a = act_pair<sizeof(T) == 2>(acc[i], act);
+        const uint64_t a = acc[i];
         float a0, a1;
         unpack2(a, a0, a1);
         T* dst = orow + (long)(ox0 + i) * C;

@@ -100,19 +100,31 @@ dwconv_act_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
         }
       }
     }
+    // activation on the whole strip (kStrip = 8 pairs): accurate swish on groups of four elements (common.cuh)
+    if (act == kActSwish) {
+#pragma unroll
+      for (int i = 0; i < kStrip; i += 2) {
+#ifdef TFIMM_FAST_ACT
+        acc[i] = swish_fast2(acc[i]);
+        acc[i + 1] = swish_fast2(acc[i + 1]);
+#else
+        swish4(acc[i], acc[i + 1]);
+#endif
+      }
+    } else if (act != kActNone) {
+#pragma unroll
+      for (int i = 0; i < kStrip; ++i) {
+        float a0, a1;
+        unpack2(acc[i], a0, a1);
+        acc[i] = pack2(apply_act<false>(a0, act), apply_act<false>(a1, act));
+      }
+    }
     if (c_ok) {
       __nv_bfloat16* orow = out + (((long)b * Ho + oy) * Wo + ox0 + sx) * C + c;
 #pragma unroll
       for (int i = 0; i < kStrip; ++i) {
         if (ox0 + sx + i < Wo) {
-          uint64_t a;
-          if (act == kActSwish) a = swish_fast2(acc[i]);
-          else if (act == kActNone) a = acc[i];
-          else {
-            float a0, a1;
-            unpack2(acc[i], a0, a1);
-            a = pack2(apply_act<false>(a0, act), apply_act<false>(a1, act));
-          }
+          const uint64_t a = acc[i];
           float a0, a1;
           unpack2(a, a0, a1);
           const uint32_t packed = pack_bf16x2(a0, a1);

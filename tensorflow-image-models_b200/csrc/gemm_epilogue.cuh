@@ -61,14 +61,29 @@ __device__ __forceinline__ void apply_vec(uint64_t (&v)[CH / 2], const float* __
 
 template <int NP>
 __device__ __forceinline__ void apply_act_pairs(uint64_t (&v)[NP], int act) {
+  static_assert(NP % 2 == 0, "activations are evaluated on groups of four elements");
   switch (act) {
     case kActGelu:
 #pragma unroll
-      for (int j = 0; j < NP; ++j) v[j] = gelu_tanh2(v[j]);
+      for (int j = 0; j < NP; j += 2) {
+#ifdef TFIMM_FAST_ACT
+        v[j] = gelu_tanh2(v[j]);
+        v[j + 1] = gelu_tanh2(v[j + 1]);
+#else
+        gelu4(v[j], v[j + 1]);
+#endif
+      }
       break;
     case kActSwish:
 #pragma unroll
-      for (int j = 0; j < NP; ++j) v[j] = swish_fast2(v[j]);
+      for (int j = 0; j < NP; j += 2) {
+#ifdef TFIMM_FAST_ACT
+        v[j] = swish_fast2(v[j]);
+        v[j + 1] = swish_fast2(v[j + 1]);
+#else
+        swish4(v[j], v[j + 1]);
+#endif
+      }
       break;
     case kActNone:
       break;
