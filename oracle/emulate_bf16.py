@@ -352,9 +352,15 @@ _EMULATED = ("gemm", "conv_gemm", "layernorm", "layernorm_patch2x2", "patch_merg
 
 
 @contextmanager
-def emulated_ops():
-    """Inside the block every ``tfimm.backend.ops`` launcher is the exact-arithmetic torch version above."""
+def emulated_ops(arithmetic=torch.float64):
+    """Inside the block every ``tfimm.backend.ops`` launcher is the exact-arithmetic torch version above.
+    ``arithmetic=torch.float32`` evaluates the same graph with the same bf16 storage points in plain fp32: a second,
+    equally legitimate "ideal" bf16 implementation whose distance from the float64 one is the DIVERGENCE FLOOR of
+    bf16 storage (rounding decisions of ~2 % of the stored elements flip on a 1e-7 perturbation and cascade)."""
     from tfimm.backend import ops
+
+    global _HP
+    saved_hp, _HP = _HP, arithmetic
 
     missing = [n for n in dir(ops) if callable(getattr(ops, n)) and not n.startswith("_") and n not in _EMULATED
                and n not in ("act_code", "same_pad", "conv_geometry", "attention_bf16_supported", "Optional") and
@@ -368,5 +374,6 @@ def emulated_ops():
         with torch.no_grad():
             yield
     finally:
+        _HP = saved_hp
         for n, f in saved.items():
             setattr(ops, n, f)

@@ -141,41 +141,13 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   return d;
 }
 
-// swish(x) = x * sigmoid(x) = x * (0.5 * tanh(x / 2) + 0.5): ONE MUFU op per element (tanh.approx, rel. error 2^-11)
-// instead of ex2 + rcp -- the swish epilogues of the MBConv GEMMs / depthwise kernels are MUFU-throughput bound
-// (16 MUFU lanes per SM per clock).
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint64_t swish_fast2(uint64_t x) {
-  float h0, h1;
-  unpack2(mul2(x, splat2(0.5f)), h0, h1);
-  return mul2(x, fma2(pack2(tanh_approx(h0), tanh_approx(h1)), splat2(0.5f), splat2(0.5f)));
-}
-// erf-GELU through ONE MUFU op: Phi(x) = 1/2 + 1/2 tanh(g(x)) holds exactly for g = atanh(erf(x / sqrt 2)); g is fitted
-// by the odd quintic x (a + b x^2 + c x^4) on |x| <= 6 (minimax for the error of x Phi: 2.5e-5 -- the usual two-term
-// "tanh GELU" is 4.7e-4 off the erf form), the argument is clamped because the quintic turns over beyond |x| ~ 11.
-// With tanh.approx (rel. error 2^-11) the result is within 2.5e-4 |x| of the exact erf GELU.  6 FMA-pipe operations
-// + 2 MUFU per PAIR: MUFU bound at 16 elements/clk/SM, against 12.5 measured for a pure-FMA degree-6 erf polynomial
-// (9 FMA-pipe operations per element) and 8 for the erfc formula with ex2 + rcp (4 MUFU per pair).
-__device__ __forceinline__ uint64_t gelu_tanh2(uint64_t x) {
-  float x0, x1;
-  unpack2(x, x0, x1);
-  const uint64_t xc = pack2(fminf(fmaxf(x0, -6.0f), 6.0f), fminf(fmaxf(x1, -6.0f), 6.0f));
-  const uint64_t t = mul2(xc, xc);
-  uint64_t p = fma2(splat2(-3.51517266e-04f), t, splat2(3.70056492e-02f));
-  p = fma2(p, t, splat2(7.97507880e-01f));
-  float g0, g1;
-  unpack2(mul2(xc, p), g0, g1);
-  return mul2(x, fma2(pack2(tanh_approx(g0), tanh_approx(g1)), splat2(0.5f), splat2(0.5f)));
-}
-
 // ---- accurate activations for the tensor-core epilogues (packed pairs, groups of FOUR elements) ----
 // The bf16 parity budget (tests/test_parity_budget_gpu.py) needs every value to be right to ~1e-5 BEFORE it is rounded
 // to bf16: a pre-rounding error d flips the rounding of a fraction d/ulp of the elements by a whole ulp, i.e. it adds
 // noise of variance d*ulp against the ulp^2/12 inherent to bf16 storage -- tanh.approx (2^-11) would DOUBLE the noise.
+// (Round 1 shipped one-MUFU tanh.approx forms: 2.5e-4 |x| off for GELU, 12-25 % of the stored values off by an ulp;
+// measured cost of the accurate forms on B200, same box: ViT-B 25.8 -> 25.1 K img/s, ConvNeXt-B 18.3 -> 17.7 K,
+// EfficientNet-B4 9.2 -> 8.6 K.)
 // Both activations are written as x * sigma with sigma = 1 / (1 + 2^u):
 //   * 2^u is one MUFU.EX2 (rel. error 2^-22);
 //   * the division is shared by four elements: 1/(d0 d1 d2 d3) is ONE MUFU.RCP, the four quotients are recovered with

@@ -47,12 +47,7 @@ __device__ __forceinline__ void act_strip(uint64_t (&acc)[N], int act) {
   if (kBf16 && act == kActSwish && N % 2 == 0) {
 #pragma unroll
     for (int i = 0; i < N; i += 2) {
-#ifdef TFIMM_FAST_ACT
-      acc[i] = swish_fast2(acc[i]);
-      acc[i + 1] = swish_fast2(acc[i + 1]);
-#else
       swish4(acc[i], acc[i + 1]);
-#endif
     }
     return;
   }

@@ -104,12 +104,7 @@ dwconv_act_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
     if (act == kActSwish) {
 #pragma unroll
       for (int i = 0; i < kStrip; i += 2) {
-#ifdef TFIMM_FAST_ACT
-        acc[i] = swish_fast2(acc[i]);
-        acc[i + 1] = swish_fast2(acc[i + 1]);
-#else
         swish4(acc[i], acc[i + 1]);
-#endif
       }
     } else if (act != kActNone) {
 #pragma unroll

@@ -66,23 +66,13 @@ __device__ __forceinline__ void apply_act_pairs(uint64_t (&v)[NP], int act) {
     case kActGelu:
 #pragma unroll
       for (int j = 0; j < NP; j += 2) {
-#ifdef TFIMM_FAST_ACT
-        v[j] = gelu_tanh2(v[j]);
-        v[j + 1] = gelu_tanh2(v[j + 1]);
-#else
         gelu4(v[j], v[j + 1]);
-#endif
       }
       break;
     case kActSwish:
 #pragma unroll
       for (int j = 0; j < NP; j += 2) {
-#ifdef TFIMM_FAST_ACT
-        v[j] = swish_fast2(v[j]);
-        v[j + 1] = swish_fast2(v[j + 1]);
-#else
         swish4(v[j], v[j + 1]);
-#endif
       }
       break;
     case kActNone:

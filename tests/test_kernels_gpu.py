@@ -242,10 +242,13 @@ def test_attention_bf16(B, N, H):
     ref, _ = _attn_ref(qkv, B, N, H, dh, dh ** -0.5)
     err = (out.float() - ref).abs().max().item()
     assert err < 3e-2, err   # P is rounded to bf16 before the PV product; output rounded to bf16
-    # against the emulation that rounds P the same way: only the output rounding (2^-9 relative) remains
-    from oracle import emulate_bf16
-    emu = emulate_bf16.attention(qkv, B, N, H, dh, dh ** -0.5).float()
-    assert (out.float() - emu).abs().max().item() < 2.0 ** -8 * emu.abs().max().item() + 1e-6
+    if N <= 256:
+        # tcgen05 kernel vs the emulation that rounds P the same way (global row max): only the output rounding
+        # (2^-9 relative) remains.  The resident-KV kernel for longer sequences rounds P per 64-key block of its
+        # online softmax, so it is only held to the bound above.
+        from oracle import emulate_bf16
+        emu = emulate_bf16.attention(qkv, B, N, H, dh, dh ** -0.5).float()
+        assert (out.float() - emu).abs().max().item() < 2.0 ** -8 * emu.abs().max().item() + 1e-6
 
 
 def test_attention_f32_with_bias_mask_probs():
@@ -624,3 +627,46 @@ def test_implicit_gemm_conv(B, H, W, C, N, ks, stride, mode):
     tol = 3e-3 if out.dtype == torch.float32 else 2e-2 + 4e-3 * ref.abs().max().item()
     assert (out.float() - ref).abs().max().item() < tol
 
+
+
+@pytest.mark.parametrize("act", ["gelu", "swish"])
+@pytest.mark.parametrize("block_n", [2, 128])
+def test_gemm_activation_epilogue_is_faithfully_rounded(act, block_n):
+    """bf16 outputs of the fused GEMM + activation epilogue are the CORRECTLY ROUNDED exact values, or their bf16
+    neighbour, and differ from the correct rounding on < 1 % of the elements: the accurate 4-element GELU / swish
+    (common.cuh) are good to ~4e-6 before rounding.  (The tanh.approx forms of round 1 flipped 12 % / 25 %.)"""
+    ops = _ops()
+    M, N, K = 1024, 512, 128
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.7).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5 * 2.0).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = ops.gemm(a, w, bias=bias, act=act, block_n=block_n)
+    torch.cuda.synchronize()
+    y = a.double() @ w.double().t() + bias.double()
+    ref = 0.5 * y * (1.0 + torch.erf(y / 2.0 ** 0.5)) if act == "gelu" else y * torch.sigmoid(y)
+    want = ref.to(torch.bfloat16)
+    flips = (out != want).float().mean().item()
+    # neighbours: |out - ref| never exceeds one bf16 spacing at that magnitude (2^-7 relative, 2^-133 absolute floor)
+    worst = ((out.double() - ref).abs() / (ref.abs() * 2.0 ** -7 + 1e-30)).max().item()
+    print(f"{act} block_n={block_n}: {100 * flips:.3f}% of the bf16 outputs differ from the correct rounding, "
+          f"worst error {worst:.3f} bf16 spacings")
+    assert flips < 1e-2 and worst <= 1.0
+
+
+def test_dwconv_swish_is_faithfully_rounded():
+    ops = _ops()
+    B, H, W, C = 2, 24, 32, 128
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    wgt = torch.randn(9, C, device="cuda", generator=g) / 3
+    bias = torch.randn(C, device="cuda", generator=g)
+    out = ops.dwconv_bias_act(x, wgt, bias, 3, 1, "same", act="swish")
+    torch.cuda.synchronize()
+    wt = wgt.double().view(3, 3, C).permute(2, 0, 1)[:, None]
+    y = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), wt, bias.double(), padding=1, groups=C).permute(0, 2, 3, 1)
+    ref = y * torch.sigmoid(y)
+    flips = (out != ref.to(torch.bfloat16)).float().mean().item()
+    worst = ((out.double() - ref).abs() / (ref.abs() * 2.0 ** -7 + 1e-30)).max().item()
+    print(f"dwconv swish: {100 * flips:.3f}% flips, worst {worst:.3f} spacings")
+    assert flips < 1e-2 and worst <= 1.0

@@ -2,19 +2,21 @@
 
 Error metric is the reference's own (tests/test_timm.py:71): max|a-b| / (max|b| + 1e-6); plain
 max|a-b| is printed next to it.  Tolerances:
-  * precision="fp32": 2e-5  (north_star: 1e-5 -- we assert 2e-5 to leave room for fp32
-    accumulation-order noise over K up to 3072; observed values are printed)
-  * precision="bf16": north_star asks 1e-3.  bf16 operands carry 2^-9 relative rounding per GEMM
-    input, which compounds over 12-24 blocks; we assert the level the arithmetic can deliver
-    (see BF16_TOL) and report the measured number in DESIGN.md instead of tuning the metric.
+  * precision="fp32": 1e-5, north_star's own bound (measured on B200: 0.3-2e-6)
+  * precision="bf16": north_star asks 1e-3, which no implementation that STORES activations in bf16 can meet (the
+    ideal one -- exact arithmetic, same storage points -- is 3-7e-3 from the fp32 reference, see
+    tests/test_parity_budget_gpu.py).  Asserted here: ~1.3x the value measured on B200 for each family, so that a
+    regression shows: ViT / Swin 1e-2 (measured 5-7e-3), ConvNeXt 7e-3 (4.5e-3), BN families 8e-3 (3-4e-3).
 """
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
-FP32_TOL = 2e-5
-BF16_TOL = 1.5e-2
+FP32_TOL = 1e-5
+BF16_TOL = 1e-2     # ViT / Swin
+BF16_TOL_CONVNEXT = 7e-3
+BF16_TOL_BN = 8e-3  # EfficientNet / ResNet families (bf16 activation stream, BatchNorm folded)
 
 
 def _nerr(out, ref):
@@ -133,7 +135,7 @@ def test_convnext_bf16_parity(name):
     _, _, _, out, ref = _run(name, "convnext", "bf16", 2)
     rel, ab = _nerr(out, ref)
     print(f"{name} bf16: normalised {rel:.3e} abs {ab:.3e}")
-    assert rel < BF16_TOL
+    assert rel < BF16_TOL_CONVNEXT
 
 
 def test_convnext_return_features():
@@ -212,7 +214,7 @@ def test_efficientnet_bf16_parity(name, size):
     _, _, _, out, ref = _run(name, "efficientnet", "bf16", 2, {"input_size": (size, size)})
     rel, ab = _nerr(out, ref)
     print(f"{name} bf16: normalised {rel:.3e} abs {ab:.3e}")
-    assert rel < 3e-2  # bf16 activation stream through 16-32 BN-folded blocks
+    assert rel < BF16_TOL_BN
 
 
 @pytest.mark.parametrize("name", ["resnet18", "resnet50", "resnet50d", "resnext50_32x4d", "seresnet50", "ecaresnet26t",
@@ -236,7 +238,7 @@ def test_resnet_norm_blur_and_wide_group_variants(name, overrides, precision):
     _, _, _, out, ref = _run(name, "resnet", precision, 2, overrides)
     rel, ab = _nerr(out, ref)
     print(f"{name} {precision}: normalised {rel:.3e} abs {ab:.3e}")
-    assert rel < (FP32_TOL if precision == "fp32" else BF16_TOL)
+    assert rel < (FP32_TOL if precision == "fp32" else BF16_TOL_BN)
 
 
 @pytest.mark.parametrize("name", ["resnet50", "resnext50_32x4d"])
@@ -244,7 +246,7 @@ def test_resnet_bf16_parity(name):
     _, _, _, out, ref = _run(name, "resnet", "bf16", 2)
     rel, ab = _nerr(out, ref)
     print(f"{name} bf16: normalised {rel:.3e} abs {ab:.3e}")
-    assert rel < 3e-2
+    assert rel < BF16_TOL_BN
 
 
 def _golden_cases():
@@ -279,7 +281,7 @@ def test_engine_matches_committed_golden_logits(fixture, precision):
     out = model(images.cuda())
     rel, ab = _nerr(out, torch.from_numpy(data["logits"]))
     print(f"{fixture} {precision}: normalised {rel:.3e} abs {ab:.3e}")
-    assert rel < (FP32_TOL if precision == "fp32" else 3e-2)
+    assert rel < (FP32_TOL if precision == "fp32" else BF16_TOL)
 
 
 def test_cuda_graph_replay_matches_eager():

@@ -71,7 +71,7 @@ def _swin_timm_names(sd, depths):
 
 
 @pytest.mark.parametrize("arch", ["resnet50", "vit", "swin"])
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1.2e-2)])
 def test_pytorch_state_dict_loaded_into_engine_reproduces_pytorch_logits(arch, precision, tol):
     import torchvision
 
@@ -139,7 +139,7 @@ def test_return_features_efficientnet_and_resnet(name, family, overrides):
     mb.load_weights_dict(w)
     yb, fb = mb(x.cuda(), return_features=True)
     assert list(fb.keys()) == list(ofeats.keys())
-    assert _nerr(fb["logits"], ofeats["logits"]) < 3e-2
+    assert _nerr(fb["logits"], ofeats["logits"]) < 8e-3
 
 
 @pytest.mark.parametrize("name,family,overrides", [
@@ -172,7 +172,10 @@ def test_nb_classes_and_in_channels_changes_preserve_outputs(name, family, overr
     # nb_classes = 0: the classifier is removed and the model returns the features
     nocls = tfimm.create_model(name, precision="fp32", device="cuda", nb_classes=0, **overrides)
     tfimm.models.transfer_weights(src, nocls)
-    assert _nerr(nocls(x3), f_src["features"]) < 1e-5
+    feats = f_src["features"]
+    if feats.dim() == 4:   # ResNet reports the un-pooled feature map (resnet.py:570-584); the head pools it
+        feats = feats.float().mean(dim=(1, 2))
+    assert _nerr(nocls(x3), feats) < 1e-5
 
     # in_channels = 1: first conv summed over the input channels -> grey image == grey image repeated 3x
     grey = params.test_images(2, h, wd, 1).cuda()
