@@ -385,30 +385,48 @@ __global__ void se_gate_kernel(const float* __restrict__ pooled_sum, float inv_h
   for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pooled_sum[(long)b * C + c] * inv_hw;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-  for (int r = warp; r < rd; r += warps) {
-    float acc = 0.f, acc1 = 0.f;
-    int c = lane;
-    for (; c + 32 < C; c += 64) {
-      acc = fmaf(mean[c], __ldg(w_reduce + (long)r * C + c), acc);
-      acc1 = fmaf(mean[c + 32], __ldg(w_reduce + (long)r * C + c + 32), acc1);
+  // Both FCs are latency-bound (weights come from L2, ~300 clk per dependent load): keep many independent loads in
+  // flight -- four rows of w_reduce per warp at a time, C walked in steps of 128 -> 16 loads per lane per round.
+  for (int r0 = warp; r0 < rd; r0 += 4 * warps) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* wr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wr[i] = w_reduce + (long)min(r0 + i * warps, rd - 1) * C;
+    for (int c0 = 0; c0 < C; c0 += 128) {
+      float m[4], w[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + lane + 32 * j;
+        m[j] = c < C ? mean[c] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i][j] = c < C ? __ldg(wr[i] + c) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i] = fmaf(m[j], w[i][j], acc[i]);
     }
-    if (c < C) acc = fmaf(mean[c], __ldg(w_reduce + (long)r * C + c), acc);
-    acc = warp_sum(acc + acc1);
-    if (lane == 0) hid[r] = apply_act<true>(acc + b_reduce[r], act);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = warp_sum(acc[i]);
+      const int r = r0 + i * warps;
+      if (lane == 0 && r < rd) hid[r] = apply_act<true>(a + b_reduce[r], act);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    // w_expand is [rd][C]: consecutive threads read consecutive channels (coalesced); 4 independent chains
-    float a0 = b_expand[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // w_expand is [rd][C]: consecutive threads read consecutive channels (coalesced); 8 independent loads per round
+    float a[8] = {b_expand[c], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int r = 0;
-    for (; r + 4 <= rd; r += 4) {
-      a0 = fmaf(hid[r], __ldg(w_expand + (long)r * C + c), a0);
-      a1 = fmaf(hid[r + 1], __ldg(w_expand + (long)(r + 1) * C + c), a1);
-      a2 = fmaf(hid[r + 2], __ldg(w_expand + (long)(r + 2) * C + c), a2);
-      a3 = fmaf(hid[r + 3], __ldg(w_expand + (long)(r + 3) * C + c), a3);
+    for (; r + 8 <= rd; r += 8) {
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = __ldg(w_expand + (long)(r + i) * C + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(hid[r + i], w[i], a[i]);
     }
-    for (; r < rd; ++r) a0 = fmaf(hid[r], __ldg(w_expand + (long)r * C + c), a0);
-    gate[(long)b * C + c] = apply_act<true>((a0 + a1) + (a2 + a3), gate_act);
+    for (; r < rd; ++r) a[0] = fmaf(hid[r], __ldg(w_expand + (long)r * C + c), a[0]);
+    gate[(long)b * C + c] = apply_act<true>(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])), gate_act);
   }
 }
 

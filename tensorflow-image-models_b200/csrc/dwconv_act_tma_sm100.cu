@@ -24,10 +24,13 @@ constexpr int kSlab = 64;        // channels per CTA
 constexpr int kStrip = 8;        // outputs per strip
 constexpr int kWarps = 8;
 
-template <int KS, int STRIDE>
+// SHAPE: output tile per CTA.  0: 8 x 32 (stride 1) / 8 x 16 (stride 2) for large maps; 1: half as wide; 2: half as
+// wide and 4 rows -- EfficientNet's late stages run on 24 x 24 and 12 x 12 maps, where the large tile computes 1.3x /
+// 3.6x more pixels than exist (B4 @ 380: the 12 x 12 x 1632 depthwise launches ran at 0.7 TB/s).
+template <int KS, int STRIDE, int SHAPE>
 struct DwTmaCfg {
-  static constexpr int TH = 8;
-  static constexpr int TW = STRIDE == 1 ? 32 : 16;
+  static constexpr int TH = SHAPE == 2 ? 4 : 8;
+  static constexpr int TW = (STRIDE == 1 ? 32 : 16) / (SHAPE == 0 ? 1 : 2);
   static constexpr int IH = (TH - 1) * STRIDE + KS;
   static constexpr int IW = (TW - 1) * STRIDE + KS;
   static constexpr int kHaloBytes = IH * IW * kSlab * 2;
@@ -39,12 +42,12 @@ __device__ __forceinline__ uint64_t bf16x2_as_f32x2(uint32_t u) {
   return pack2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
-template <int KS, int STRIDE>
+template <int KS, int STRIDE, int SHAPE>
 __global__ void __launch_bounds__(kWarps * 32)
 dwconv_act_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ wgt /*[KS*KS][C]*/,
                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, float* __restrict__ pool_sum,
                       int C, int Ho, int Wo, int pad_t, int pad_l, int tiles_x, int tiles_y, int cslabs, int act) {
-  using Cfg = DwTmaCfg<KS, STRIDE>;
+  using Cfg = DwTmaCfg<KS, STRIDE, SHAPE>;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t* halo = reinterpret_cast<const uint32_t*>(smem);                       // [IH][IW][32] bf16x2
   float* red = reinterpret_cast<float*>(smem + ((Cfg::kHaloBytes + 15) / 16) * 16);     // [kWarps][64]
@@ -145,17 +148,17 @@ dwconv_act_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
   }
 }
 
-template <int KS, int STRIDE>
+template <int KS, int STRIDE, int SHAPE>
 int launch_dw_tma(const void* x, const float* wgt, const float* bias, void* out, float* pool_sum, int B, int H, int W,
                   int C, int pad_t, int pad_l, int Ho, int Wo, int act, cudaStream_t stream) {
-  using Cfg = DwTmaCfg<KS, STRIDE>;
+  using Cfg = DwTmaCfg<KS, STRIDE, SHAPE>;
   CUtensorMap tmap;
   const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
   const uint32_t box[4] = {(uint32_t)kSlab, (uint32_t)Cfg::IW, (uint32_t)Cfg::IH, 1u};
   int rc = make_tmap(&tmap, x, kBF16, 4, dims, strides, box, "dwconv input", /*swizzle_bytes=*/0);
   if (rc != kOk) return rc;
-  auto kernel = dwconv_act_tma_kernel<KS, STRIDE>;
+  auto kernel = dwconv_act_tma_kernel<KS, STRIDE, SHAPE>;
   static unsigned long long attr_devs = 0;
   if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -179,10 +182,24 @@ int dwconv_bias_act_tma(const void* x, int dtype, const float* wgt, const float*
                         cudaStream_t stream) {
   if (dtype != kBF16 || C % 8 != 0 || !(ks == 3 || ks == 5) || !(stride == 1 || stride == 2)) return kUnsupported;
   if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0 || pad_t < 0 || pad_l < 0) return kUnsupported;
-  if (ks == 3 && stride == 1) return launch_dw_tma<3, 1>(x, wgt, bias, out, pool_sum, B, H, W, C, pad_t, pad_l, Ho, Wo, act, stream);
-  if (ks == 3) return launch_dw_tma<3, 2>(x, wgt, bias, out, pool_sum, B, H, W, C, pad_t, pad_l, Ho, Wo, act, stream);
-  if (stride == 1) return launch_dw_tma<5, 1>(x, wgt, bias, out, pool_sum, B, H, W, C, pad_t, pad_l, Ho, Wo, act, stream);
-  return launch_dw_tma<5, 2>(x, wgt, bias, out, pool_sum, B, H, W, C, pad_t, pad_l, Ho, Wo, act, stream);
+  // tile shape: the one that computes the fewest pixels beyond the map (ties: the larger tile)
+  const int tw0 = stride == 1 ? 32 : 16;
+  auto padded = [&](int th, int tw) { return (long)((Ho + th - 1) / th * th) * ((Wo + tw - 1) / tw * tw); };
+  int shape = 0;
+  long best = padded(8, tw0);
+  if (padded(8, tw0 / 2) < best) { best = padded(8, tw0 / 2); shape = 1; }
+  if (padded(4, tw0 / 2) < best) { best = padded(4, tw0 / 2); shape = 2; }
+#define TFIMM_DWT(KS_, ST_)                                                                                          \
+  do {                                                                                                               \
+    if (shape == 0) return launch_dw_tma<KS_, ST_, 0>(x, wgt, bias, out, pool_sum, B, H, W, C, pad_t, pad_l, Ho, Wo, act, stream); \
+    if (shape == 1) return launch_dw_tma<KS_, ST_, 1>(x, wgt, bias, out, pool_sum, B, H, W, C, pad_t, pad_l, Ho, Wo, act, stream); \
+    return launch_dw_tma<KS_, ST_, 2>(x, wgt, bias, out, pool_sum, B, H, W, C, pad_t, pad_l, Ho, Wo, act, stream);     \
+  } while (0)
+  if (ks == 3 && stride == 1) TFIMM_DWT(3, 1);
+  if (ks == 3) TFIMM_DWT(3, 2);
+  if (stride == 1) TFIMM_DWT(5, 1);
+  TFIMM_DWT(5, 2);
+#undef TFIMM_DWT
 }
 
 }  // namespace tfimm

@@ -149,8 +149,10 @@ def test_baseline_config_at_its_own_batch_through_cuda_graph(family, name, batch
     fwd = model.cuda_graph(batch)
     y = fwd(x.cuda()).float().cpu().clone()
     y_again = fwd(x.cuda()).float().cpu()
-    if family == "efficientnet":   # the fused squeeze (global pool) uses fp32 atomics: sums differ in the last bits
-        assert _nerr(y_again, y)[0] < 1e-3
+    if family == "efficientnet":
+        # the fused squeeze (global pool) accumulates with fp32 atomics: the sums differ in their last bits from run
+        # to run, and that 1e-7 perturbation grows to the bf16 divergence floor (see the module docstring)
+        assert _nerr(y_again, y)[0] < 3e-3
     else:
         assert torch.equal(y, y_again)                               # replay is deterministic
     idx = torch.linspace(0, batch - 1, nref).round().long()          # first, last and in between: every CTA wave
