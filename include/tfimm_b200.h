@@ -127,6 +127,15 @@ int tfimm_b200_window_attention_bf16(const void* qkv, void* out, const float* bi
                                      const int* labels, int B, int nw_img, int N, int H, int dh, float scale,
                                      void* stream);
 
+/* Same operator on the tcgen05 tensor cores (head_dim 32, N <= 52 tokens per window): two windows per 128-row UMMA
+ * tile, S = Q K^T and O = P V with fp32 accumulators in tensor memory, cp.async row gather / 64-byte row scatter.
+ * bias_pad: fp32 [H][64][64] (the gathered relative-position bias, rows / columns >= N unused);
+ * maskbits: uint64 [nw_img][64], bit j of entry (w, i) set when tokens i and j of window w are in different shift
+ * regions (the -100 entries of swin.py:249-273), or NULL for unshifted blocks. */
+int tfimm_b200_window_attention_tc_bf16(const void* qkv, void* out, const float* bias_pad, const int* row_map,
+                                        const void* maskbits, int B, int nw_img, int N, int H, int dh, float scale,
+                                        void* stream);
+
 /* Non-overlapping p x p patch gather (im2col of Conv2D(k=p, s=p, VALID)); out (B*H/p*W/p, Kpad),
  * column order (ky, kx, c), zero-padded to Kpad.  Optional fused create_preprocessing:
  * v = (x*scale - mean[c]) * inv_std[c] (tfimm/models/factory.py:153-169).

@@ -182,6 +182,15 @@ def window_attention(qkv, bias, row_map, labels, B, nw_img, N, H, dh, scale):
     return attention(qkv, B * nw_img, N, H, dh, scale, bias=bias, mask=mask, row_map=row_map, nw_img=nw_img)
 
 
+def window_attention_tc(qkv, bias_pad, row_map, maskbits, B, nw_img, N, H, dh, scale):
+    mask = None
+    if maskbits is not None:
+        bits = (maskbits[:, :N, None] >> torch.arange(N, device=maskbits.device)[None, None, :]) & 1
+        mask = torch.where(bits.bool(), -100.0, 0.0).to(_HP)
+    return attention(qkv, B * nw_img, N, H, dh, scale, bias=bias_pad[:, :N, :N], mask=mask, row_map=row_map,
+                     nw_img=nw_img)
+
+
 def patchify(img, p, out_dtype, mean=None, inv_std=None, scale=1.0):
     B, H, W, C = img.shape
     x = img.to(_HP)
@@ -346,7 +355,7 @@ def scale_add_act_(x, gate, shortcut, act):
 
 
 _EMULATED = ("gemm", "conv_gemm", "layernorm", "layernorm_patch2x2", "patch_merge_ln", "attention", "attention_cls",
-             "window_attention", "patchify", "assemble_tokens", "cast", "dwconv_ln", "dwconv_bias_act",
+             "window_attention", "window_attention_tc", "patchify", "assemble_tokens", "cast", "dwconv_ln", "dwconv_bias_act",
              "global_avg_pool", "im2col", "group_norm", "blur_pool", "se_gate", "scale_channels_", "pool2d",
              "grouped_conv", "eca_gate", "scale_add_act_")
 

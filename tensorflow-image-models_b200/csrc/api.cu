@@ -59,6 +59,8 @@ int attention_f32(const float*, float*, const float*, const float*, int, long, i
                   const int*, int, cudaStream_t);
 int window_attention_bf16(const void*, void*, const float*, const int*, const int*, int, int, int, int, int,
                           float, cudaStream_t);
+int window_attention_tc_bf16(const void*, void*, const float*, const int*, const unsigned long long*, int, int, int, int,
+                             int, float, cudaStream_t);
 int patchify(const void*, int, void*, int, int, int, int, int, int, int, float, const float*, const float*,
              cudaStream_t);
 int assemble_tokens(const void*, int, const float*, const float*, const float*, void*, int, int, int, int, int,
@@ -150,6 +152,14 @@ int tfimm_b200_window_attention_bf16(const void* qkv, void* out, const float* bi
                                      const int* labels, int B, int nw_img, int N, int H, int dh, float scale,
                                      void* stream) {
   return tfimm::window_attention_bf16(qkv, out, bias, row_map, labels, B, nw_img, N, H, dh, scale, S(stream));
+}
+
+int tfimm_b200_window_attention_tc_bf16(const void* qkv, void* out, const float* bias_pad, const int* row_map,
+                                        const void* maskbits, int B, int nw_img, int N, int H, int dh, float scale,
+                                        void* stream) {
+  return tfimm::window_attention_tc_bf16(qkv, out, bias_pad, row_map,
+                                         reinterpret_cast<const unsigned long long*>(maskbits), B, nw_img, N, H, dh,
+                                         scale, S(stream));
 }
 
 int tfimm_b200_patchify(const void* img, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C,

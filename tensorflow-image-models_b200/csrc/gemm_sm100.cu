@@ -340,8 +340,8 @@ bool prefer_pair(int M, int N) {
 
 }  // namespace
 
-int gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, const float* bias, void* C, int ldc, int M, int N,
-                     int K, int act, cudaStream_t stream);
+int gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
+                     void* C, int ldc, int M, int N, int K, int act, cudaStream_t stream);
 
 int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const float* bias,
                        const float* gamma, const void* residual, int ldr, void* C, int ldc, int M,
@@ -351,9 +351,9 @@ int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const flo
   TFIMM_CHECK_ARG(K % 8 == 0, "gemm: K must be a multiple of 8 (got %d)", K);
   TFIMM_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0, "gemm: bias must be 16-byte aligned");
   TFIMM_CHECK_ARG(gamma == nullptr || (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0, "gemm: gamma must be 16-byte aligned");
-  if (force_block_n == 0 && K <= 64 && out_dtype == kBF16 && residual == nullptr && gamma == nullptr) {
+  if (force_block_n == 0 && K <= 64 && out_dtype == kBF16 && gamma == nullptr && act_post == 0) {
     // short contraction: streaming mma.sync kernel (gemm_skinny.cu); kUnsupported = shape outside its envelope
-    const int st = gemm_bf16_skinny(A, lda, W, ldw, bias, C, ldc, M, N, K, act, stream);
+    const int st = gemm_bf16_skinny(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, act, stream);
     if (st != kUnsupported) return st;
   }
   GemmParams p{};

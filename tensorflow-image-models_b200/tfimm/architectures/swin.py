@@ -231,16 +231,29 @@ class SwinTransformer(Model):
                     if labels is not None:
                         lab = torch.from_numpy(labels).view(-1, ws * ws)
                         mask = torch.where(lab[:, None, :] != lab[:, :, None], -100.0, 0.0).float().contiguous().to(dev)
+                    bits = None
+                    if labels is not None and ws * ws <= 52:
+                        # bit j of (window w, token i): tokens i and j lie in different shift regions (the -100 entries)
+                        diff = (lab[:, :, None] != lab[:, None, :]).to(torch.int64)              # (nW, n, n)
+                        packed = (diff << torch.arange(ws * ws, dtype=torch.int64)[None, None, :]).sum(dim=-1)
+                        bits = torch.zeros((lab.shape[0], 64), dtype=torch.int64)
+                        bits[:, :ws * ws] = packed
+                        bits = bits.contiguous().to(dev)
                     tables[(ws, shift)] = (
                         torch.from_numpy(row_map).to(dev),
                         torch.from_numpy(labels).to(dev) if labels is not None else None,
                         mask,
+                        bits,
                     )
                 n = ws * ws
                 table = self.params[f"{p}/attn/relative_position_bias_table"].float()
                 bias = table[index].view(n, n, heads).permute(2, 0, 1).contiguous()  # tf.gather + transpose
+                bias_pad = None
+                if n <= 52:  # tcgen05 window-attention kernel: 16-byte aligned rows of 64
+                    bias_pad = torch.zeros((heads, 64, 64), device=dev, dtype=torch.float32)
+                    bias_pad[:, :n, :n] = bias
                 st["blocks"].append(dict(
-                    ws=ws, shift=shift, tables=tables[(ws, shift)], bias=bias,
+                    ws=ws, shift=shift, tables=tables[(ws, shift)], bias=bias, bias_pad=bias_pad,
                     n1=(self._vec(f"{p}/norm1/gamma"), self._vec(f"{p}/norm1/beta")),
                     qkv_w=self._dense_weight(f"{p}/attn/qkv/kernel"),
                     qkv_b=self._vec(f"{p}/attn/qkv/bias") if c.qkv_bias else None,
@@ -265,8 +278,10 @@ class SwinTransformer(Model):
 
     # ------------------------------------------------------------------ forward
     def _window_attention(self, qkv, blk, B, nw, n, heads, dh):
-        row_map, labels, mask = blk["tables"]
+        row_map, labels, mask, bits = blk["tables"]
         scale = dh ** -0.5
+        if qkv.dtype == torch.bfloat16 and dh == 32 and n <= 52:
+            return ops.window_attention_tc(qkv, blk["bias_pad"], row_map, bits, B, nw, n, heads, dh, scale)
         if qkv.dtype == torch.bfloat16 and dh == 32 and n <= 64:
             return ops.window_attention(qkv, blk["bias"], row_map, labels, B, nw, n, heads, dh, scale)
         # generic path: fp32 SIMT kernel (precision="fp32", or windows larger than 64 tokens)

@@ -70,7 +70,7 @@ def _call(name, *args, flops=0.0, nbytes=0.0):
         e0.record()
         _lib.check(fn(*args), name)
         e1.record()
-        trace.append((name.replace("tfimm_b200_", "").replace("conv_bf16", "gemm_bf16"), e0, e1, float(flops),
+        trace.append((name.replace("tfimm_b200_", "").replace("conv_bf16", "gemm_bf16").replace("window_attention_tc_bf16", "window_attention_bf16"), e0, e1, float(flops),
                       float(nbytes)))
     else:
         _lib.check(fn(*args), name)
@@ -309,6 +309,21 @@ def window_attention(qkv, bias, row_map, labels, B, nw_img, N, H, dh, scale):
     out = torch.empty((B * nw_img * N, H * dh), device=qkv.device, dtype=qkv.dtype)
     _call("tfimm_b200_window_attention_bf16", qkv.data_ptr(), out.data_ptr(), bias.data_ptr(), row_map.data_ptr(),
           _ptr(labels), B, nw_img, N, H, dh, float(scale), _stream(),
+          flops=4.0 * B * nw_img * H * N * N * dh, nbytes=_nbytes(qkv, out))
+    return out
+
+
+def window_attention_tc(qkv, bias_pad, row_map, maskbits, B, nw_img, N, H, dh, scale):
+    """Swin (shifted-)window attention on tcgen05 (head_dim 32, N <= 52): token-ordered qkv (B*nw_img*N, 3*H*dh) ->
+    (B*nw_img*N, H*dh).  bias_pad: fp32 (H, 64, 64); maskbits: int64 (nw_img, 64) or None (see window_mask_bits)."""
+    _cuda(qkv, bias_pad, row_map, maskbits)
+    assert qkv.shape == (B * nw_img * N, 3 * H * dh) and qkv.is_contiguous() and qkv.dtype == torch.bfloat16
+    assert bias_pad.shape == (H, 64, 64) and bias_pad.dtype == torch.float32 and bias_pad.is_contiguous()
+    assert row_map.dtype == torch.int32 and (maskbits is None or (maskbits.dtype == torch.int64
+                                                                 and maskbits.shape == (nw_img, 64)))
+    out = torch.empty((B * nw_img * N, H * dh), device=qkv.device, dtype=qkv.dtype)
+    _call("tfimm_b200_window_attention_tc_bf16", qkv.data_ptr(), out.data_ptr(), bias_pad.data_ptr(),
+          row_map.data_ptr(), _ptr(maskbits), B, nw_img, N, H, dh, float(scale), _stream(),
           flops=4.0 * B * nw_img * H * N * N * dh, nbytes=_nbytes(qkv, out))
     return out
 

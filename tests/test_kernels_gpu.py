@@ -397,7 +397,7 @@ def test_window_attention_bf16(h, w, ws, shift, H):
     from tfimm.architectures.swin import window_tables
 
     ops = _ops()
-    B, dh = 3, 32
+    B, dh = 5, 32
     n, nw, C = ws * ws, (h // ws) * (w // ws), H * 32
     g = torch.Generator(device="cuda").manual_seed(h * w + shift)
     qkv = (torch.randn(B * h * w, 3 * C, device="cuda", generator=g) * 1.2).to(torch.bfloat16)
@@ -420,6 +420,27 @@ def test_window_attention_bf16(h, w, ws, shift, H):
     ref = torch.roll(ow, (shift, shift), (1, 2)).reshape(B * h * w, C)
     err = (out.float() - ref).abs().max().item()
     assert err < 3e-2, err
+    # tcgen05 kernel (two windows per UMMA tile): padded bias table + per-row 64-bit region masks
+    if n <= 52:
+        bias_pad = torch.zeros(H, 64, 64, device="cuda")
+        bias_pad[:, :n, :n] = bias
+        bits = None
+        if labels is not None:
+            lb = torch.from_numpy(labels).view(nw, n)
+            diff = (lb[:, :, None] != lb[:, None, :]).to(torch.int64)
+            packed = (diff << torch.arange(n, dtype=torch.int64)[None, None, :]).sum(dim=-1)
+            bits = torch.zeros(nw, 64, dtype=torch.int64)
+            bits[:, :n] = packed
+            bits = bits.cuda()
+        for Bt in (B, 1, 5):   # odd window counts: the last item holds a single window
+            q2 = qkv[: Bt * h * w]
+            out_tc = ops.window_attention_tc(q2, bias_pad, rm, bits, Bt, nw, n, H, dh, dh ** -0.5)
+            torch.cuda.synchronize()
+            err_tc = (out_tc.float() - ref[: Bt * h * w]).abs().max().item() if Bt <= B else 0.0
+            assert err_tc < 3e-2, (Bt, err_tc)
+            from oracle import emulate_bf16
+            emu = emulate_bf16.window_attention_tc(q2, bias_pad, rm, bits, Bt, nw, n, H, dh, dh ** -0.5).float()
+            assert (out_tc.float() - emu).abs().max().item() < 2.0 ** -7 * emu.abs().max().item() + 1e-6
     # fp32 kernel with the same row map
     out32 = ops.attention(qkv.float(), B * nw, n, H, dh, dh ** -0.5, bias=bias, mask=mask, row_map=rm, nw_img=nw)
     torch.cuda.synchronize()
@@ -679,3 +700,35 @@ def test_dwconv_swish_is_faithfully_rounded():
     flips, worst = _faithful(out, ref)
     print(f"dwconv swish: {100 * flips:.3f}% flips, worst {worst:.3f} x max(bf16 spacing, 5e-6)")
     assert flips < 2e-2 and worst <= 1.0
+
+
+@pytest.mark.parametrize("M,K,N", [(9000, 24, 144), (5000, 32, 192), (4096, 64, 512), (4100, 48, 24), (70001, 56, 336),
+                                   (4097, 8, 8), (6000, 40, 72)])
+@pytest.mark.parametrize("act", [None, "swish", "gelu", "relu6"])
+def test_gemm_short_contraction_streaming_kernel(M, K, N, act):
+    """K <= 64, bf16 out, no residual: the mma.sync streaming kernel (gemm_skinny.cu) behind the same entry point."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    a_full = torch.randn(M, K + 8, device="cuda", generator=g).to(torch.bfloat16)
+    a = a_full[:, :K]                                   # row stride != K: lda is honoured
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = ops.gemm(a, w, bias=bias, act=act)
+    torch.cuda.synchronize()
+    from oracle import emulate_bf16
+    ref = emulate_bf16.gemm(a, w, bias=bias, act=act).float()
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16
+    assert (out.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-5
+    assert (out != ref.to(torch.bfloat16)).float().mean().item() < 2e-2
+    # the tcgen05 path gives the same numbers (forced through block_n)
+    out2 = ops.gemm(a, w, bias=bias, act=act, block_n=64)
+    assert (out.float() - out2.float()).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-5
+    # bf16 residual, also in place
+    res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    ref_r = emulate_bf16.gemm(a, w, bias=bias, act=act, residual=res).float()
+    out_r = ops.gemm(a, w, bias=bias, act=act, residual=res)
+    buf = res.clone()
+    ops.gemm(a, w, bias=bias, act=act, residual=buf, out=buf)
+    torch.cuda.synchronize()
+    assert (out_r.float() - ref_r).abs().max().item() <= 2.0 ** -7 * ref_r.abs().max().item() + 1e-5
+    assert torch.equal(out_r, buf)

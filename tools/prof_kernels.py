@@ -47,8 +47,28 @@ def main(case):
         qkv = torch.randn(B * 196, 1536, device="cuda", generator=g).to(torch.bfloat16)
         bias = torch.randn(16, 49, 49, device="cuda", generator=g)
         rm, lab = window_tables(14, 14, 7, 3)
-        rm, lab = torch.from_numpy(rm).cuda(), torch.from_numpy(lab).cuda()
-        fn = lambda: ops.window_attention(qkv, bias, rm, lab, B, 4, 49, 16, 32, 32 ** -0.5)
+        lb = torch.from_numpy(lab).view(4, 49)
+        diff = (lb[:, :, None] != lb[:, None, :]).to(torch.int64)
+        bits = torch.zeros(4, 64, dtype=torch.int64)
+        bits[:, :49] = (diff << torch.arange(49, dtype=torch.int64)[None, None, :]).sum(dim=-1)
+        rm, bits = torch.from_numpy(rm).cuda(), bits.cuda()
+        bias_pad = torch.zeros(16, 64, 64, device="cuda")
+        bias_pad[:, :49, :49] = bias
+        fn = lambda: ops.window_attention_tc(qkv, bias_pad, rm, bits, B, 4, 49, 16, 32, 32 ** -0.5)
+    elif case == "window_attn0":  # Swin-B stage 0, shifted: 64 windows x 4 heads per image
+        from tfimm.architectures.swin import window_tables
+
+        qkv = torch.randn(B * 3136, 384, device="cuda", generator=g).to(torch.bfloat16)
+        bias = torch.randn(4, 49, 49, device="cuda", generator=g)
+        rm, lab = window_tables(56, 56, 7, 3)
+        lb = torch.from_numpy(lab).view(64, 49)
+        diff = (lb[:, :, None] != lb[:, None, :]).to(torch.int64)
+        bits = torch.zeros(64, 64, dtype=torch.int64)
+        bits[:, :49] = (diff << torch.arange(49, dtype=torch.int64)[None, None, :]).sum(dim=-1)
+        rm, bits = torch.from_numpy(rm).cuda(), bits.cuda()
+        bias_pad = torch.zeros(4, 64, 64, device="cuda")
+        bias_pad[:, :49, :49] = bias
+        fn = lambda: ops.window_attention_tc(qkv, bias_pad, rm, bits, B, 64, 49, 4, 32, 32 ** -0.5)
     elif case == "dwconv_act":   # EfficientNet-B4 stage 1 (380 px): 95x95x192, k3 s1
         x = torch.randn(B, 95, 95, 192, device="cuda", generator=g).to(torch.bfloat16)
         wt = torch.randn(9, 192, device="cuda", generator=g) / 3
