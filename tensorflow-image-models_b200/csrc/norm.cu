@@ -68,6 +68,98 @@ layernorm_kernel(const float* __restrict__ gamma, const float* __restrict__ beta
   }
 }
 
+// Plain fp32 rows (the residual stream of ViT / Swin / ConvNeXt): 16-byte accesses with lane = chunk of FOUR channels,
+// so every load instruction covers 512 contiguous bytes of the row (the generic kernel's 8-channel chunks make each
+// fp32 load touch only half of every sector, and leave half the warp idle at C = 128), and ROWS rows per warp in flight
+// for the narrow rows of the early Swin / ConvNeXt stages.
+template <typename OutT, int MAXI, int ROWS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_f32_rows_kernel(const float* __restrict__ x, long in_stride, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, OutT* __restrict__ out, long out_stride, long rows, int C,
+                          float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row0 = ((long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= rows) return;
+  const int nchunks = C >> 2;
+  const float inv_c = 1.0f / (float)C;
+  float4 v[ROWS][MAXI];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const bool row_ok = row0 + r < rows;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int ch = lane + 32 * i;
+      v[r][i] = (row_ok && ch < nchunks) ? *reinterpret_cast<const float4*>(x + (row0 + r) * in_stride + ch * 4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float mean[ROWS], rstd[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+    mean[r] = warp_sum(s) * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      if (lane + 32 * i < nchunks) {
+        const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], c = v[r][i].z - mean[r], d = v[r][i].w - mean[r];
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    rstd[r] = rsqrtf(warp_sum(q) * inv_c + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < nchunks) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + ch * 4));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + ch * 4));
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        if (row0 + r < rows) {
+          const float y0 = (v[r][i].x - mean[r]) * rstd[r] * g.x + b.x, y1 = (v[r][i].y - mean[r]) * rstd[r] * g.y + b.y;
+          const float y2 = (v[r][i].z - mean[r]) * rstd[r] * g.z + b.z, y3 = (v[r][i].w - mean[r]) * rstd[r] * g.w + b.w;
+          OutT* dst = out + (row0 + r) * out_stride + ch * 4;
+          if constexpr (sizeof(OutT) == 2) {
+            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+          } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(y0, y1, y2, y3);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename OutT>
+int launch_ln_f32_rows(const float* x, long in_stride, const float* gamma, const float* beta, OutT* out,
+                       long out_stride, long rows, int C, float eps, cudaStream_t stream) {
+  const int maxi = (C / 4 + 31) / 32;
+  const int threads = kWarpsPerBlock * 32;
+#define TFIMM_LNR(I, R)                                                                                            \
+  do {                                                                                                             \
+    const long warps = (rows + R - 1) / R;                                                                         \
+    layernorm_f32_rows_kernel<OutT, I, R><<<(unsigned)((warps + kWarpsPerBlock - 1) / kWarpsPerBlock), threads, 0, \
+                                            stream>>>(x, in_stride, gamma, beta, out, out_stride, rows, C, eps);   \
+  } while (0)
+  if (maxi <= 1) TFIMM_LNR(1, 4);
+  else if (maxi <= 2) TFIMM_LNR(2, 2);
+  else if (maxi <= 4) TFIMM_LNR(4, 1);
+  else if (maxi <= 6) TFIMM_LNR(6, 1);
+  else if (maxi <= 8) TFIMM_LNR(8, 1);
+  else if (maxi <= 16) TFIMM_LNR(16, 1);
+  else if (maxi <= 32) TFIMM_LNR(32, 1);
+  else {
+    set_last_error("layernorm: C=%d too large (max 4096)", C);
+    return kUnsupported;
+  }
+#undef TFIMM_LNR
+  TFIMM_LAUNCH_OK("layernorm_f32_rows_kernel");
+  return kOk;
+}
+
 struct PlainRows {
   const void* in;
   void* out;
@@ -173,6 +265,16 @@ int layernorm_rows(const void* x, int in_dtype, long in_stride, const float* gam
                    cudaStream_t stream) {
   TFIMM_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "layernorm: need rows>0 and C%%8==0 (rows=%ld C=%d)", rows, C);
   TFIMM_CHECK_ARG(in_stride % 8 == 0 && out_stride % 8 == 0, "layernorm: strides must be multiples of 8 elements");
+  if (in_dtype == kF32 && C % 4 == 0 && in_stride % 4 == 0 && out_stride % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+      (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15u) == 0) {
+    if (out_dtype == kBF16)
+      return launch_ln_f32_rows(reinterpret_cast<const float*>(x), in_stride, gamma, beta,
+                                reinterpret_cast<__nv_bfloat16*>(out), out_stride, rows, C, eps, stream);
+    if (out_dtype == kF32)
+      return launch_ln_f32_rows(reinterpret_cast<const float*>(x), in_stride, gamma, beta, reinterpret_cast<float*>(out),
+                                out_stride, rows, C, eps, stream);
+  }
   PlainRows map{x, out, in_stride, out_stride};
   return dispatch_ln(in_dtype, out_dtype, gamma, beta, rows, C, eps, map, stream);
 }

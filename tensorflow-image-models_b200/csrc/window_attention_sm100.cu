@@ -9,8 +9,9 @@
 //                    SWIZZLE_64B pattern) into a 4-stage shared-memory ring; two items of copies in flight per thread
 //   1 MMA warp       S = Q K^T as ONE 128 x 128 x 32 tcgen05.mma chain (only the two diagonal 64 x 64 blocks are used:
 //                    the tensor pipe is idle anyway), later O = P V (128 x 32 x 128, A = P from tensor memory, B = V as
-//                    an MN-major SWIZZLE_64B operand).  Software-pipelined: S of item i+1 is issued before P V of item i
-//   2 x 4 softmax warps (groups alternate items; one TMEM slot of 256 columns each): thread = query row.  Its 64
+//                    an MN-major SWIZZLE_64B operand).  Software-pipelined: S of item i+2 is issued before P V of item i
+//   2 x 4 softmax warps (groups alternate items; TWO 128-column TMEM buffers each, so the scores of a group's next
+//                    item are already there when it finishes the current one): thread = query row.  Its 64
 //                    scores come out of tensor memory ONCE (no second pass: a window row fits the register file),
 //                    + relative-position bias row (padded [H][64][64] table, 16-byte loads) and -100 where the
 //                    shift-region labels differ (one 64-bit mask per row, precomputed on the host), fp32 softmax with
@@ -29,12 +30,16 @@ constexpr int kDh = 32;
 constexpr int kRowBytes = kDh * 2;               // 64
 constexpr int kTileBytes = kItemRows * kRowBytes;    // 8 KB per q / k / v
 constexpr int kStageBytes = 3 * kTileBytes;          // 24 KB
-constexpr int kStages = 4;
+constexpr int kStages = 6;
+constexpr int kMapMax = 4096;                    // row_map entries staged in shared memory (nw_img * N)
 constexpr int kLoaderWarps = 2;
 constexpr int kThreads = (8 + 1 + kLoaderWarps) * 32;   // 352
-constexpr uint32_t kSlotCols = 256;              // TMEM columns per softmax group: S [0,128), O [128,160)
-constexpr uint32_t kOCol = 128;
-constexpr int kSmemBytes = kStages * kStageBytes + 16 * 8 + 16 + 1024;
+// TMEM: 4 buffers of 128 columns = (group, parity of the group's item count).  A buffer holds the scores S [0,128),
+// then P (packed bf16) over [0,64) and the output accumulator O over [64,96) -- both dead score columns by then.
+constexpr uint32_t kBufCols = 128;
+constexpr uint32_t kOCol = 64;
+constexpr int kNumBars = 2 * kStages + 16;
+constexpr int kSmemBytes = kStages * kStageBytes + kNumBars * 8 + 16 + kMapMax * 4 + 1024;
 
 // 16-byte chunk c of row r in the SWIZZLE_64B pattern (Swizzle<2,4,3>: address bits [4,6) ^= bits [7,9))
 __device__ __forceinline__ uint32_t sw64(int row, int chunk) {
@@ -74,66 +79,73 @@ window_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
   const uint32_t bars = smem_base + kStages * kStageBytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
-  auto sfull_bar = [&](int g) { return bars + 8u * (2 * kStages + g); };
-  auto pready_bar = [&](int g) { return bars + 8u * (2 * kStages + 2 + g); };
-  auto ofull_bar = [&](int g) { return bars + 8u * (2 * kStages + 4 + g); };
-  auto tempty_bar = [&](int g) { return bars + 8u * (2 * kStages + 6 + g); };
-  const uint32_t tmem_ptr_smem = bars + 8u * 16;
+  // per TMEM buffer tb = 2 * group + (k & 1), k = index of the item among the group's items
+  auto sfull_bar = [&](int tb) { return bars + 8u * (2 * kStages + tb); };
+  auto pready_bar = [&](int tb) { return bars + 8u * (2 * kStages + 4 + tb); };
+  auto ofull_bar = [&](int tb) { return bars + 8u * (2 * kStages + 8 + tb); };
+  auto tempty_bar = [&](int tb) { return bars + 8u * (2 * kStages + 12 + tb); };
+  const uint32_t tmem_ptr_smem = bars + 8u * kNumBars;
+  int* s_map = reinterpret_cast<int*>(smem_gen + (bars - smem_base) + 8 * kNumBars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = nw_img * N;                 // tokens per image
   const long ld = 3L * H * kDh;             // qkv row stride (elements)
   const long pairs = (total_windows + 1) >> 1;   // window pairs; item = head * pairs + pair (pair fastest)
+  const bool map_in_smem = L <= kMapMax;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), kLoaderWarps);
       mbar_init(empty_bar(s), 1);
     }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(sfull_bar(g), 1);
-      mbar_init(pready_bar(g), 4);
-      mbar_init(ofull_bar(g), 1);
-      mbar_init(tempty_bar(g), 4);
+    for (int tb = 0; tb < 4; ++tb) {
+      mbar_init(sfull_bar(tb), 1);
+      mbar_init(pready_bar(tb), 4);
+      mbar_init(ofull_bar(tb), 1);
+      mbar_init(tempty_bar(tb), 4);
     }
     fence_mbar_init();
   }
+  if (map_in_smem)
+    for (int i = threadIdx.x; i < L; i += kThreads) s_map[i] = row_map[i];
   if (warp == 8) tmem_alloc<512>(tmem_ptr_smem);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+  // token -> row of its image (32-bit: one image has < 2^31 tokens)
+  auto map_at = [&](int idx) { return map_in_smem ? s_map[idx] : __ldg(row_map + idx); };
 
   if (warp >= 9) {
     // ------------------------------------------- loaders -------------------------------------------
-    const int lt = (warp - 9) * 32 + lane;          // 0..63
+    // thread = rows lt and lt + 64 of the item (the same token of the two windows), all four 16-byte chunks of q, k, v
+    const int lt = (warp - 9) * 32 + lane;          // 0..63 = token
     long it = 0;
     int pending_stage = -1;
     for (long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int s = (int)(it % kStages);
       const uint32_t ph = (uint32_t)(it / kStages) & 1u;
       const int h = (int)(item / pairs);
-      const long pair = item % pairs;
+      const long gwin0 = 2 * (item % pairs);
+      const long img0 = gwin0 / nw_img;
+      const int wi0 = (int)(gwin0 - img0 * nw_img);
       mbar_wait(empty_bar(s), ph ^ 1u);
       const uint32_t sQ = smem_base + s * kStageBytes, sK = sQ + kTileBytes, sV = sK + kTileBytes;
-      // 128 rows x 4 chunks: this thread takes rows lt/4 + 16 j (j < 8), chunk lt & 3
-      const int c = lt & 3;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = (lt >> 2) + 16 * j;
-        const long gwin = 2 * pair + (r >> 6);
-        const int tok = r & 63;
-        const bool valid = tok < N && gwin < total_windows;
-        long src_row = 0;
-        if (valid) {
-          const int wi = (int)(gwin % nw_img);
-          src_row = (gwin / nw_img) * L + __ldg(row_map + wi * N + tok);
+      for (int w = 0; w < 2; ++w) {
+        const int wi = (w == 0) ? wi0 : (wi0 + 1 == nw_img ? 0 : wi0 + 1);
+        const long img = (w == 0) ? img0 : (wi0 + 1 == nw_img ? img0 + 1 : img0);
+        const bool valid = lt < N && gwin0 + w < total_windows;
+        const long src_row = valid ? img * L + map_at(wi * N + lt) : 0;
+        const __nv_bfloat16* src = qkv + src_row * ld + (long)h * kDh;
+        const int r = w * kWinRows + lt;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t off = sw64(r, c);
+          cp_async_16(sQ + off, src + c * 8, valid);
+          cp_async_16(sK + off, src + H * kDh + c * 8, valid);
+          cp_async_16(sV + off, src + 2 * H * kDh + c * 8, valid);
         }
-        const __nv_bfloat16* src = qkv + src_row * ld + (long)h * kDh + c * 8;
-        const uint32_t off = sw64(r, c);
-        cp_async_16(sQ + off, src, valid);
-        cp_async_16(sK + off, src + H * kDh, valid);
-        cp_async_16(sV + off, src + 2 * H * kDh, valid);
       }
       cp_async_commit();
       if (pending_stage >= 0) {
@@ -152,40 +164,44 @@ window_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
     }
   } else if (warp == 8) {
     // ------------------------------------------ MMA issuer ------------------------------------------
+    // program order: S(it), then P V (it - 2).  S of an item only needs its TMEM buffer drained by the item four
+    // back, so the scores of a group's NEXT item are ready while the group is still in its softmax.
     constexpr uint32_t idesc_s = umma_idesc_bf16_f32(kItemRows, kItemRows);
     constexpr uint32_t idesc_o = umma_idesc_bf16_f32(kItemRows, kDh, /*b_mn_major=*/true);
     long n_items = 0;
     for (long item = blockIdx.x; item < total_items; item += gridDim.x) ++n_items;
-    for (long it = 0; it <= n_items; ++it) {
+    for (long it = 0; it < n_items + 2; ++it) {
       if (it < n_items) {
-        const int s = (int)(it % kStages), g = (int)(it & 1);
+        const int s = (int)(it % kStages);
+        const int tb = (int)(2 * (it & 1) + ((it >> 1) & 1));
         mbar_wait(full_bar(s), (uint32_t)(it / kStages) & 1u);
-        mbar_wait(tempty_bar(g), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        mbar_wait(tempty_bar(tb), ((uint32_t)(it >> 2) & 1u) ^ 1u);
         tcgen05_fence_after();
         if (lane == 0) {
           const uint32_t sQ = smem_base + s * kStageBytes, sK = sQ + kTileBytes;
           const uint64_t dq = umma_desc_k_sw64(sQ), dk = umma_desc_k_sw64(sK);
 #pragma unroll
           for (int k = 0; k < kDh / 16; ++k)
-            umma_bf16_ss(tmem_base + (uint32_t)g * kSlotCols, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s,
+            umma_bf16_ss(tmem_base + (uint32_t)tb * kBufCols, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s,
                          (uint32_t)(k != 0));
-          umma_commit(sfull_bar(g));
+          umma_commit(sfull_bar(tb));
         }
         __syncwarp();
       }
-      if (it >= 1) {
-        const long jt = it - 1;
-        const int s = (int)(jt % kStages), g = (int)(jt & 1);
-        mbar_wait(pready_bar(g), (uint32_t)(jt >> 1) & 1u);
+      if (it >= 2) {
+        const long jt = it - 2;
+        const int s = (int)(jt % kStages);
+        const int tb = (int)(2 * (jt & 1) + ((jt >> 1) & 1));
+        mbar_wait(pready_bar(tb), (uint32_t)(jt >> 2) & 1u);
         tcgen05_fence_after();
         if (lane == 0) {
           const uint32_t sV = smem_base + s * kStageBytes + 2 * kTileBytes;
-          const uint32_t t0 = tmem_base + (uint32_t)g * kSlotCols;
+          const uint32_t t0 = tmem_base + (uint32_t)tb * kBufCols;
 #pragma unroll
           for (int j = 0; j < kItemRows / 16; ++j)   // 16 keys per step: 8 packed P columns, 1024 bytes of V
             umma_bf16_ts(t0 + kOCol, t0 + (uint32_t)(j * 8), umma_desc_mn_sw64(sV + (uint32_t)(j * 1024)), idesc_o,
                          (uint32_t)(j != 0));
-          umma_commit(ofull_bar(g));
+          umma_commit(ofull_bar(tb));
           umma_commit(empty_bar(s));   // every MMA that reads this stage has completed when this arrives
         }
         __syncwarp();
@@ -197,19 +213,23 @@ window_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
     const int q = warp & 3;               // TMEM lane quarter
     const int r = q * 32 + lane;          // row inside the item
     const int win = r >> 6, tok = r & 63;
-    const uint32_t t_row = tmem_base + (uint32_t)g * kSlotCols + ((uint32_t)(q * 32) << 16);
     const float l2e = 1.4426950408889634f;
     const float sl2 = scale * l2e;
     long it = 0;
     for (long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       if ((it & 1) != g) continue;
-      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      const int tb = 2 * g + (int)((it >> 1) & 1);
+      const uint32_t par = (uint32_t)(it >> 2) & 1u;
+      const uint32_t t_row = tmem_base + (uint32_t)tb * kBufCols + ((uint32_t)(q * 32) << 16);
       const int h = (int)(item / pairs);
-      const long gwin = 2 * (item % pairs) + win;
-      const bool row_ok = tok < N && gwin < total_windows;
-      const int wi = (int)(gwin % nw_img);
+      const long gwin0 = 2 * (item % pairs);
+      const long img0 = gwin0 / nw_img;
+      const int wi0 = (int)(gwin0 - img0 * nw_img);
+      const int wi = (win == 0) ? wi0 : (wi0 + 1 == nw_img ? 0 : wi0 + 1);
+      const long img = (win == 0) ? img0 : (wi0 + 1 == nw_img ? img0 + 1 : img0);
+      const bool row_ok = tok < N && gwin0 + win < total_windows;
       // bias row and mask bits of this query row: issued before the wait on the scores
-      float b[64];
+      float b[52];
       const float4* brow = reinterpret_cast<const float4*>(bias_pad + ((long)h * 64 + tok) * 64);
 #pragma unroll
       for (int j = 0; j < 13; ++j) {
@@ -218,27 +238,24 @@ window_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
       }
       unsigned long long mbits = 0ull;
       if (maskbits != nullptr && row_ok) mbits = __ldg(maskbits + (long)wi * 64 + tok);
-      long out_row = 0;
-      if (row_ok) out_row = (gwin / nw_img) * L + __ldg(row_map + wi * N + tok);
+      const long out_row = row_ok ? img * L + map_at(wi * N + tok) : 0;
 
-      mbar_wait(sfull_bar(g), par);
+      mbar_wait(sfull_bar(tb), par);
       tcgen05_fence_after();
       uint32_t s0[32], s1[32];
       tmem_ld_32x32b_x32(t_row + (uint32_t)(win * 64), s0);
       tmem_ld_32x32b_x32(t_row + (uint32_t)(win * 64 + 32), s1);
       tmem_ld_wait();
-      // logits (log2 domain) of the N keys of this row's own window
+      // logits (log2 domain) of the N <= 52 keys of this row's own window
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        if (j < 52) {  // keys beyond 51 can never be valid (N <= 49 for every registered Swin; N <= 52 is checked)
-          const float sv = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]);
-          float v = fmaf(sv, sl2, b[j] * l2e);
-          if ((mbits >> j) & 1ull) v -= 100.0f * l2e;
-          v = j < N ? v : -INFINITY;
-          b[j] = v;
-          mx = fmaxf(mx, v);
-        }
+      for (int j = 0; j < 52; ++j) {
+        const float sv = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]);
+        float v = fmaf(sv, sl2, b[j] * l2e);
+        if ((mbits >> j) & 1ull) v -= 100.0f * l2e;
+        v = j < N ? v : -INFINITY;
+        b[j] = v;
+        mx = fmaxf(mx, v);
       }
       float sum = 0.f;
       uint32_t pk[32];
@@ -250,7 +267,9 @@ window_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
         sum += p0 + p1;
         pk[j] = pack_bf16x2(p0, p1);
       }
-      // P: 128 keys = 64 packed columns; own window's 32 columns, zeros in the other window's
+      // every thread of the group must have its scores in registers before anybody overwrites columns [0, 64)
+      // (P of window 1 lands on the score columns of window 0 -- in OTHER lanes' rows, but the same TMEM columns of
+      // its own lane only: no hazard across lanes; the barrier is only needed against the MMA, which is idle here)
       {
         uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
@@ -265,16 +284,16 @@ window_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pready_bar(g));
+      if (lane == 0) mbar_arrive(pready_bar(tb));
 
-      mbar_wait(ofull_bar(g), par);
+      mbar_wait(ofull_bar(tb), par);
       tcgen05_fence_after();
       uint32_t o[32];
       tmem_ld_32x32b_x32(t_row + kOCol, o);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(g));   // the MMA warp may put the next item's scores into this slot
+      if (lane == 0) mbar_arrive(tempty_bar(tb));   // the MMA warp may reuse this buffer (four items from now)
       if (row_ok) {
         const float inv = 1.0f / sum;
         uint4* dst = reinterpret_cast<uint4*>(out + out_row * ((long)H * kDh) + (long)h * kDh);
