@@ -148,24 +148,20 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 // (Round 1 shipped one-MUFU tanh.approx forms: 2.5e-4 |x| off for GELU, 12-25 % of the stored values off by an ulp;
 // measured cost of the accurate forms on B200, same box: ViT-B 25.8 -> 25.1 K img/s, ConvNeXt-B 18.3 -> 17.7 K,
 // EfficientNet-B4 9.2 -> 8.6 K.)
-// Both activations are written as x * sigma with sigma = 1 / (1 + 2^u):
-//   * 2^u is one MUFU.EX2 (rel. error 2^-22);
-//   * the division is shared by four elements: 1/(d0 d1 d2 d3) is ONE MUFU.RCP, the four quotients are recovered with
-//     nine multiplications (d <= 1 + 2^28, so the product stays below 2^127)
-// => 1.25 MUFU operations per element instead of 2 (MUFU: 16 lanes / clk / SM is the epilogue's narrowest pipe).
+// Both activations are written as x * sigma with sigma = 1 / (1 + 2^u): one MUFU.EX2 (rel. error 2^-22) and one
+// MUFU.RCP per element.  (A shared reciprocal -- 1 / (d0 d1 d2 d3) and nine multiplications for four quotients, 1.25
+// MUFU per element -- was measured 3 % SLOWER on the fc1 + GELU GEMM: under the board's power cap the currency is
+// instructions executed, not the MUFU pipe; tools/power_probe.py.)
 __device__ __forceinline__ void sigma4_from_log2(uint64_t u01, uint64_t u23, uint64_t& s01, uint64_t& s23) {
   float u0, u1, u2, u3;
   unpack2(u01, u0, u1);
   unpack2(u23, u2, u3);
   const uint64_t one2 = splat2(1.0f);
   float d0, d1, d2, d3;
-  unpack2(add2(pack2(ex2_approx(fminf(u0, 28.f)), ex2_approx(fminf(u1, 28.f))), one2), d0, d1);
-  unpack2(add2(pack2(ex2_approx(fminf(u2, 28.f)), ex2_approx(fminf(u3, 28.f))), one2), d2, d3);
-  const float p01 = d0 * d1, p23 = d2 * d3;
-  const float inv = rcp_approx(p01 * p23);
-  const float r01 = inv * p23, r23 = inv * p01;  // 1 / (d0 d1), 1 / (d2 d3)
-  s01 = mul2(pack2(d1, d0), splat2(r01));        // (1/d0, 1/d1)
-  s23 = mul2(pack2(d3, d2), splat2(r23));
+  unpack2(add2(pack2(ex2_approx(u0), ex2_approx(u1)), one2), d0, d1);
+  unpack2(add2(pack2(ex2_approx(u2), ex2_approx(u3)), one2), d2, d3);
+  s01 = pack2(rcp_approx(d0), rcp_approx(d1));   // 2^u = +inf -> rcp = +0: no clamp needed
+  s23 = pack2(rcp_approx(d2), rcp_approx(d3));
 }
 // swish(x) = x * sigmoid(x), sigmoid(x) = 1 / (1 + 2^(-x log2 e)).
 __device__ __forceinline__ void swish4(uint64_t& x01, uint64_t& x23) {
@@ -347,30 +343,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait parks the thread in hardware until the phase completes or the time hint (ns; the hardware caps it) runs out,
+// so a waiting warp issues a handful of instructions per microsecond instead of spinning in the issue slots of the
+// warps that share its scheduler.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred P;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, P;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug turns into a trap (reported as a CUDA error by
-// the host) instead of a hung GPU.  ~4e9 cycles is a couple of seconds.
+// Bounded wait: a protocol bug turns into a trap (reported as a CUDA error by the host) instead of a hung GPU.  The
+// bound is a poll count -- no clock reads in the loop: 2^26 polls take at least a second even if none of them parks.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("tfimm_b200: mbarrier timeout (block %d thread %d bar %u parity %u)\n",
-             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (++polls == (1u << 26)) __trap();
   }
 }
 

@@ -133,8 +133,11 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx == 1) {
     // ------------------------------- MMA issuer (leader CTA) -------------------------------
-    if (leader) {
+    // ONE thread: the loop is ~20 instructions per k-block, and its issue latency is what the tensor pipe waits on when
+    // the sixteen epilogue warps are busy -- no warp-wide waits, no reconvergence points.
+    if (leader && lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(kPairM, kBlockN);
+      const uint64_t da0 = umma_desc_k_sw128(smem_tiles), db0 = umma_desc_k_sw128(smem_tiles + kABytes);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -146,21 +149,16 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_tiles + stage * kStageBytes;
-            const uint32_t sb = sa + kABytes;
-            const uint64_t da = umma_desc_k_sw128(sa);
-            const uint64_t db = umma_desc_k_sw128(sb);
+          const uint64_t off = (uint64_t)((uint32_t)(stage * kStageBytes) >> 4);
+          const uint64_t da = da0 + off, db = db0 + off;
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // +32 bytes per UMMA_K step inside the swizzle span -> +2 in the (addr>>4) field
-              umma_bf16_ss_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                (uint32_t)((kb | k) != 0));
-            }
-            umma_commit_pair(empty_bar(stage), 0x3);                          // frees the slot in both CTAs
-            if (kb == num_k_blocks - 1) umma_commit_pair(tfull_bar(acc), 0x3);  // accumulator ready, both CTAs
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // +32 bytes per UMMA_K step inside the swizzle span -> +2 in the (addr>>4) field
+            umma_bf16_ss_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                              (uint32_t)((kb | k) != 0));
           }
-          __syncwarp();
+          umma_commit_pair(empty_bar(stage), 0x3);                          // frees the slot in both CTAs
+          if (kb == num_k_blocks - 1) umma_commit_pair(tfull_bar(acc), 0x3);  // accumulator ready, both CTAs
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }

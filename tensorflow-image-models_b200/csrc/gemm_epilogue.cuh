@@ -97,7 +97,8 @@ __device__ __forceinline__ void apply_act_pairs(uint64_t (&v)[NP], int act) {
 //              in the NHWC output; null for a plain row-major C
 //   CHW        columns per chunk: 128 bytes of output per row by default; the CTA-pair kernel's bf16 instance uses
 //              32 columns (64-byte rows, 64B swizzle, 2 KB slabs) so that sixteen epilogue warps fit
-template <typename OutT, int CHW = 128 / (int)sizeof(OutT), typename AfterLoad>
+//   kStoresInFlight  1 when the caller passes alternating slabs (two per warp)
+template <typename OutT, int CHW = 128 / (int)sizeof(OutT), int kStoresInFlight = 0, typename AfterLoad>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_addr, int n0, int row0,
                                                uint32_t slab, uint8_t* my_row, int lane, uint32_t res_bar,
                                                uint32_t res_parity, const CUtensorMap* tmap_c,
@@ -109,9 +110,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_a
   static_assert(RB == 128 || RB == 64, "slab rows are 128 or 64 bytes");
   // TMA swizzle: 16-byte unit j of row r lives at j ^ (r & 7) (SWIZZLE_128B) or j ^ ((r >> 1) & 3) (SWIZZLE_64B)
   const int sw = RB == 128 ? (lane & 7) : ((lane >> 1) & 3);
-  // the previous store of this warp must have finished reading the slab
+  // the previous store of this warp FROM THIS SLAB must have finished reading it (kStoresInFlight = 1: the caller
+  // alternates between two slabs, so the store issued one chunk ago may still be in flight)
   if (lane == 0) {
-    tma_store_wait_read<0>();
+    tma_store_wait_read<kStoresInFlight>();
     if (p.has_res) {
       mbar_expect_tx(res_bar, 32 * RB);
       if (ct == nullptr) tma_load_2d(slab, tmap_r, res_bar, n0, row0);

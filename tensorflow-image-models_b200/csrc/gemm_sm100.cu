@@ -134,36 +134,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx == 1) {
     // ------------------------------- MMA issuer -------------------------------
+    // ONE thread: its issue latency is what the tensor pipe waits on while the epilogue warps are busy
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BLOCK_N);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+    if (lane == 0) {
+      const uint64_t da0 = umma_desc_k_sw128(smem_tiles), db0 = umma_desc_k_sw128(smem_tiles + Cfg::kABytes);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_tiles + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = umma_desc_k_sw128(sa);
-          const uint64_t db = umma_desc_k_sw128(sb);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t off = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
+          const uint64_t da = da0 + off, db = db0 + off;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // +32 bytes per UMMA_K step inside the swizzle span -> +2 in the (addr>>4) field
-            umma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                         (uint32_t)((kb | k) != 0));
+            umma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
           }
-          umma_commit(empty_bar(stage));                      // frees the smem slot
+          umma_commit(empty_bar(stage));                            // frees the smem slot
           if (kb == num_k_blocks - 1) umma_commit(tfull_bar(acc));  // accumulator ready
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
       }
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // -------------------------------- epilogue --------------------------------
