@@ -63,6 +63,30 @@ int tfimm_b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, const f
                          const float* gamma, const void* residual, int ldr, void* C, int ldc, int M, int N,
                          int K, int act, int act_after_residual, int out_dtype, int force_block_n, void* stream);
 
+/* Dense / 1x1 conv whose INPUT rows carry a squeeze-excite gate:  C = residual + act((A * gate[row / rows_per_image]) @ W^T
+ * + bias), bf16 in / out.  gate: fp32 [n_images][K] (the sigmoid of tfimm_b200_se_gate).  The gate is applied to the A
+ * tile in shared memory between the TMA load and the tensor-core product, with the rounding of the separate pass
+ * (bf16(x * g), tfimm_b200_scale_channels) -- which, as its own kernel, read and wrote the whole expanded activation
+ * (3.4 ms of a 24 ms EfficientNet-B4 step at batch 256).  Replaces `x * gate` of SEModule.call
+ * (tfimm/layers/attention.py, used at efficientnet_blocks.py:241-248, 438-453) + the projection Conv2D that follows. */
+int tfimm_b200_gemm_bf16_gated(const void* A, int lda, const float* gate, int rows_per_image, int n_images,
+                               const void* W, int ldw, const float* bias, const void* residual, int ldr, void* C,
+                               int ldc, int M, int N, int K, int act, void* stream);
+
+/* Fused MLP block of the narrow stages:  out = residual + gamma * (act(A @ W1^T + b1) @ W2^T + b2).
+ * A:[M,C] bf16 (the normalised activations), W1:[hidden,C] bf16, W2:[C,hidden] bf16, b1:[hidden], b2:[C], gamma:[C] or
+ * NULL (ConvNeXt layer scale), residual / out:[M,C] fp32 (residual may alias out, or be NULL).  C in {128, 256},
+ * hidden a multiple of 128: other shapes return TFIMM_B200_UNSUPPORTED and the caller runs two tfimm_b200_gemm_bf16.
+ * One CTA pair per 256 rows walks the hidden dimension in chunks of 128: fc1 chunk (tcgen05, cta_group::2) ->
+ * bias + activation -> bf16 back into tensor memory -> A operand of the fc2 chunk product; the [M,hidden]
+ * activations never reach HBM (the hidden tensor is 61 % of the bytes the two-GEMM form moves at C = 128).  The
+ * rounding points are those of the two-GEMM form (bf16 hidden, fp32 accumulation in ascending k).
+ * Replaces MLP.call (tfimm/layers/transformers.py:208-214) + layer scale + shortcut in ConvNeXtBlock.call
+ * (tfimm/architectures/convnext.py:219-228) and the MLP half of SwinTransformerBlock.call (swin.py:315-318). */
+int tfimm_b200_mlp_bf16(const void* A, int lda, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
+                        const float* b2, const float* gamma, const void* residual, int ldr, void* out, int ldc, int M,
+                        int C, int hidden, int act, void* stream);
+
 /* Dense k x k convolution (+ folded-BN bias, activation, optional residual, act(x + shortcut)) as an IMPLICIT GEMM
  * on the tcgen05 tensor cores: tf.keras.layers.ZeroPadding2D(pad) + Conv2D(k, strides) (+ BatchNormalization, act)
  * at tfimm/architectures/resnet.py:129-150 (BasicBlock 3x3), 230-238 (Bottleneck conv2), 486-512 (deep stems).

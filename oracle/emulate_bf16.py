@@ -88,6 +88,22 @@ def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dty
     return _store(y, out, dt)
 
 
+def gemm_gated(a, gate, rows_per_image, w, bias=None, act=None, residual=None):
+    img = torch.arange(a.shape[0], device=a.device) // rows_per_image
+    scaled = (a.to(_HP) * gate.to(_HP)[img]).to(a.dtype)          # the product is rounded to bf16 before the GEMM
+    return gemm(scaled, w, bias=bias, act=act, residual=residual)
+
+
+def mlp_fused_supported(C, hidden):
+    return C in (128, 256) and hidden % 128 == 0 and hidden >= 256
+
+
+def mlp_fused(a, w1, b1, w2, b2, act, gamma=None, residual=None, out=None):
+    # the kernel's rounding points are those of the two-GEMM form: bf16 hidden activations, fp32 output
+    hid = gemm(a, w1, bias=b1, act=act)
+    return gemm(hid, w2, bias=b2, gamma=gamma, residual=residual, out=out, out_dtype=torch.float32)
+
+
 def conv_gemm(x, w, bias=None, ks=3, stride=1, pad=1, act=None, residual=None, act_after_residual=False,
               out_dtype=None):
     B, H, W, C = x.shape
@@ -354,7 +370,7 @@ def scale_add_act_(x, gate, shortcut, act):
     return x
 
 
-_EMULATED = ("gemm", "conv_gemm", "layernorm", "layernorm_patch2x2", "patch_merge_ln", "attention", "attention_cls",
+_EMULATED = ("gemm", "gemm_gated", "mlp_fused", "mlp_fused_supported", "conv_gemm", "layernorm", "layernorm_patch2x2", "patch_merge_ln", "attention", "attention_cls",
              "window_attention", "window_attention_tc", "patchify", "assemble_tokens", "cast", "dwconv_ln", "dwconv_bias_act",
              "global_avg_pool", "im2col", "group_norm", "blur_pool", "se_gate", "scale_channels_", "pool2d",
              "grouped_conv", "eca_gate", "scale_add_act_")

@@ -61,6 +61,10 @@ int window_attention_bf16(const void*, void*, const float*, const int*, const in
                           float, cudaStream_t);
 int window_attention_tc_bf16(const void*, void*, const float*, const int*, const unsigned long long*, int, int, int, int,
                              int, float, cudaStream_t);
+int gemm_bf16_gated_dispatch(const void*, int, const float*, int, int, const void*, int, const float*, const void*, int,
+                             void*, int, int, int, int, int, cudaStream_t);
+int mlp_fused_bf16(const void*, int, const void*, int, const float*, const void*, int, const float*, const float*,
+                   const void*, int, void*, int, int, int, int, int, cudaStream_t);
 int patchify(const void*, int, void*, int, int, int, int, int, int, int, float, const float*, const float*,
              cudaStream_t);
 int assemble_tokens(const void*, int, const float*, const float*, const float*, void*, int, int, int, int, int,
@@ -160,6 +164,20 @@ int tfimm_b200_window_attention_tc_bf16(const void* qkv, void* out, const float*
   return tfimm::window_attention_tc_bf16(qkv, out, bias_pad, row_map,
                                          reinterpret_cast<const unsigned long long*>(maskbits), B, nw_img, N, H, dh,
                                          scale, S(stream));
+}
+
+int tfimm_b200_gemm_bf16_gated(const void* A, int lda, const float* gate, int rows_per_image, int n_images,
+                               const void* W, int ldw, const float* bias, const void* residual, int ldr, void* C,
+                               int ldc, int M, int N, int K, int act, void* stream) {
+  return tfimm::gemm_bf16_gated_dispatch(A, lda, gate, rows_per_image, n_images, W, ldw, bias, residual, ldr, C, ldc, M,
+                                         N, K, act, S(stream));
+}
+
+int tfimm_b200_mlp_bf16(const void* A, int lda, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
+                        const float* b2, const float* gamma, const void* residual, int ldr, void* out, int ldc, int M,
+                        int C, int hidden, int act, void* stream) {
+  return tfimm::mlp_fused_bf16(A, lda, W1, ldw1, b1, W2, ldw2, b2, gamma, residual, ldr, out, ldc, M, C, hidden, act,
+                               S(stream));
 }
 
 int tfimm_b200_patchify(const void* img, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C,

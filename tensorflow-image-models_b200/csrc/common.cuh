@@ -152,22 +152,37 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 // MUFU.RCP per element.  (A shared reciprocal -- 1 / (d0 d1 d2 d3) and nine multiplications for four quotients, 1.25
 // MUFU per element -- was measured 3 % SLOWER on the fc1 + GELU GEMM: under the board's power cap the currency is
 // instructions executed, not the MUFU pipe; tools/power_probe.py.)
+// kSharedRcp: ONE MUFU.RCP for four elements -- 1 / (d0 d1 d2 d3), the four quotients recovered with nine
+// multiplications (u clamped to 28 so that the product stays below 2^127) -- 1.25 MUFU per element instead of 2, for
+// kernels whose activation warps are bound by the MUFU pipe (16 lanes / clk / SM) rather than by issue slots.
+template <bool kSharedRcp = false>
 __device__ __forceinline__ void sigma4_from_log2(uint64_t u01, uint64_t u23, uint64_t& s01, uint64_t& s23) {
   float u0, u1, u2, u3;
   unpack2(u01, u0, u1);
   unpack2(u23, u2, u3);
   const uint64_t one2 = splat2(1.0f);
   float d0, d1, d2, d3;
-  unpack2(add2(pack2(ex2_approx(u0), ex2_approx(u1)), one2), d0, d1);
-  unpack2(add2(pack2(ex2_approx(u2), ex2_approx(u3)), one2), d2, d3);
-  s01 = pack2(rcp_approx(d0), rcp_approx(d1));   // 2^u = +inf -> rcp = +0: no clamp needed
-  s23 = pack2(rcp_approx(d2), rcp_approx(d3));
+  if constexpr (kSharedRcp) {
+    unpack2(add2(pack2(ex2_approx(fminf(u0, 28.f)), ex2_approx(fminf(u1, 28.f))), one2), d0, d1);
+    unpack2(add2(pack2(ex2_approx(fminf(u2, 28.f)), ex2_approx(fminf(u3, 28.f))), one2), d2, d3);
+    const float p01 = d0 * d1, p23 = d2 * d3;
+    const float inv = rcp_approx(p01 * p23);
+    const float r01 = inv * p23, r23 = inv * p01;  // 1 / (d0 d1), 1 / (d2 d3)
+    s01 = mul2(pack2(d1, d0), splat2(r01));        // (1/d0, 1/d1)
+    s23 = mul2(pack2(d3, d2), splat2(r23));
+  } else {
+    unpack2(add2(pack2(ex2_approx(u0), ex2_approx(u1)), one2), d0, d1);
+    unpack2(add2(pack2(ex2_approx(u2), ex2_approx(u3)), one2), d2, d3);
+    s01 = pack2(rcp_approx(d0), rcp_approx(d1));   // 2^u = +inf -> rcp = +0: no clamp needed
+    s23 = pack2(rcp_approx(d2), rcp_approx(d3));
+  }
 }
 // swish(x) = x * sigmoid(x), sigmoid(x) = 1 / (1 + 2^(-x log2 e)).
+template <bool kSharedRcp = false>
 __device__ __forceinline__ void swish4(uint64_t& x01, uint64_t& x23) {
   const uint64_t nl2e = splat2(-1.4426950408889634f);
   uint64_t s01, s23;
-  sigma4_from_log2(mul2(x01, nl2e), mul2(x23, nl2e), s01, s23);
+  sigma4_from_log2<kSharedRcp>(mul2(x01, nl2e), mul2(x23, nl2e), s01, s23);
   x01 = mul2(x01, s01);
   x23 = mul2(x23, s23);
 }
@@ -185,9 +200,10 @@ __device__ __forceinline__ uint64_t gelu_neg_log2_odds(uint64_t x) {
   q = fma2(q, t, splat2(2.3020482063293457f));
   return mul2(mul2(x, splat2(-1.0f)), q);
 }
+template <bool kSharedRcp = false>
 __device__ __forceinline__ void gelu4(uint64_t& x01, uint64_t& x23) {
   uint64_t s01, s23;
-  sigma4_from_log2(gelu_neg_log2_odds(x01), gelu_neg_log2_odds(x23), s01, s23);
+  sigma4_from_log2<kSharedRcp>(gelu_neg_log2_odds(x01), gelu_neg_log2_odds(x23), s01, s23);
   x01 = mul2(x01, s01);
   x23 = mul2(x23, s23);
 }
@@ -351,7 +367,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P;\n"
+#ifdef TFIMM_TRYWAIT_NO_HINT
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n"
+#endif
       "selp.u32 %0, 1, 0, P;\n"
       "}\n"
       : "=r"(ok)
@@ -359,12 +379,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug turns into a trap (reported as a CUDA error by the host) instead of a hung GPU.  The
-// bound is a poll count -- no clock reads in the loop: 2^26 polls take at least a second even if none of them parks.
+// Bounded wait: a protocol bug turns into a trap (reported as a CUDA error by the host) instead of a hung GPU: the
+// cycle counter is read once on entry and then only every 256th poll, ~4e9 cycles is a couple of seconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls == (1u << 26)) __trap();
+    if ((++polls & 255u) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
 

@@ -16,6 +16,11 @@ struct GemmParams {
   int act;
   int has_res;
   int act_post;  // 1: activation applied after the residual add (ResNet: act(x + shortcut))
+  // Squeeze-excite gate folded into the A operand (gemm_sm100.cu, gated instances): row m of A is multiplied by
+  // a_scale[m / a_rows_per_img][k] (fp32 [a_imgs][K]) and rounded back to bf16 in shared memory, between the TMA load
+  // and the MMA -- the values the separate scale_channels pass used to write to HBM.
+  const float* a_scale;
+  int a_rows_per_img, a_imgs;
   // Implicit convolution (gemm_sm100.cu): the A operand is not a matrix but the NHWC input itself.  A tile's 128
   // rows are a patch of cv_pb images x cv_ph rows x cv_pw columns of OUTPUT pixels; k-block kb is tap
   // (ky, kx) = kb / (C/64) and 64 input channels, fetched as ONE 4-D TMA box whose out-of-bounds elements are
@@ -59,20 +64,20 @@ __device__ __forceinline__ void apply_vec(uint64_t (&v)[CH / 2], const float* __
   }
 }
 
-template <int NP>
+template <int NP, bool kSharedRcp = false>
 __device__ __forceinline__ void apply_act_pairs(uint64_t (&v)[NP], int act) {
   static_assert(NP % 2 == 0, "activations are evaluated on groups of four elements");
   switch (act) {
     case kActGelu:
 #pragma unroll
       for (int j = 0; j < NP; j += 2) {
-        gelu4(v[j], v[j + 1]);
+        gelu4<kSharedRcp>(v[j], v[j + 1]);
       }
       break;
     case kActSwish:
 #pragma unroll
       for (int j = 0; j < NP; j += 2) {
-        swish4(v[j], v[j + 1]);
+        swish4<kSharedRcp>(v[j], v[j + 1]);
       }
       break;
     case kActNone:

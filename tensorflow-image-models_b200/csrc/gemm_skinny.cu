@@ -28,7 +28,8 @@ __device__ __forceinline__ uint32_t sk_off(int row, int chunk) {
 __global__ void __launch_bounds__(kSkWarps * 32, 3)
 gemm_bf16_skinny_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ W, int ldw,
                         const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, int ldr,
-                        __nv_bfloat16* __restrict__ C, int ldc, int M, int N, int K, int act, int n_rows_w) {
+                        __nv_bfloat16* __restrict__ C, int ldc, int M, int N, int K, int act, int n_rows_w,
+                        const float* __restrict__ gate, int rows_per_img, int imgs) {
   extern __shared__ __align__(128) uint8_t smem[];
   // [W: n_rows_w x 128 B][A buffers: 2 x 128 x 128 B][bias: n_rows_w floats]
   const uint32_t sW = smem_u32(smem);
@@ -76,6 +77,32 @@ gemm_bf16_skinny_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv
         if (ks < ksteps) {
           const int row = warp * 16 + (lane & 15);
           ldmatrix_x4(a_base + sk_off(row, ks * 2 + (lane >> 4)), af[ks][0], af[ks][1], af[ks][2], af[ks][3]);
+        }
+      }
+      if (gate != nullptr) {
+        // squeeze-excite gate on the A fragments: element (row, k) *= gate[row / rows_per_img][k], rounded to bf16 like
+        // the separate scale pass.  A lane holds rows g, g + 8 and k = 16 ks + 2 t + {0, 1, 8, 9} of every k-step.
+        long i0 = (row0 + g) / rows_per_img, i1 = (row0 + g + 8) / rows_per_img;
+        i0 = i0 < imgs ? i0 : imgs - 1;
+        i1 = i1 < imgs ? i1 : imgs - 1;
+        const float* g0 = gate + i0 * K + 2 * t;
+        const float* g1 = gate + i1 * K + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          if (ks < ksteps) {
+            const int k = ks * 16;
+            const bool lo_ok = k + 2 * t < K, hi_ok = k + 8 + 2 * t < K;   // K % 8 == 0: a pair is in or out as a whole
+            const float2 z = make_float2(0.f, 0.f);
+            const float2 a_lo = lo_ok ? __ldg(reinterpret_cast<const float2*>(g0 + k)) : z;
+            const float2 a_hi = hi_ok ? __ldg(reinterpret_cast<const float2*>(g0 + k + 8)) : z;
+            const float2 b_lo = lo_ok ? __ldg(reinterpret_cast<const float2*>(g1 + k)) : z;
+            const float2 b_hi = hi_ok ? __ldg(reinterpret_cast<const float2*>(g1 + k + 8)) : z;
+            float2 x;
+            x = unpack_bf16x2(af[ks][0]); af[ks][0] = pack_bf16x2(x.x * a_lo.x, x.y * a_lo.y);
+            x = unpack_bf16x2(af[ks][1]); af[ks][1] = pack_bf16x2(x.x * b_lo.x, x.y * b_lo.y);
+            x = unpack_bf16x2(af[ks][2]); af[ks][2] = pack_bf16x2(x.x * a_hi.x, x.y * a_hi.y);
+            x = unpack_bf16x2(af[ks][3]); af[ks][3] = pack_bf16x2(x.x * b_hi.x, x.y * b_hi.y);
+          }
         }
       }
       const bool r0_ok = row0 + g < M, r1_ok = row0 + g + 8 < M;
@@ -140,7 +167,8 @@ gemm_bf16_skinny_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv
 
 // Returns kUnsupported (without setting an error) for shapes outside this kernel: the caller uses the tcgen05 path.
 int gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
-                     void* C, int ldc, int M, int N, int K, int act, cudaStream_t stream) {
+                     void* C, int ldc, int M, int N, int K, int act, cudaStream_t stream, const float* gate,
+                     int rows_per_img, int imgs) {
   if (K > 64 || K % 8 != 0 || N % 8 != 0 || N > kSkNMax || M < 4096) return kUnsupported;
   if (lda % 8 != 0 || ldw % 8 != 0 || ldc % 8 != 0) return kUnsupported;
   if (residual != nullptr && (ldr % 2 != 0 || (reinterpret_cast<uintptr_t>(residual) & 3u))) return kUnsupported;
@@ -160,7 +188,7 @@ int gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, const float
   gemm_bf16_skinny_kernel<<<grid, kSkWarps * 32, smem, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W), ldw, bias,
       reinterpret_cast<const __nv_bfloat16*>(residual), ldr, reinterpret_cast<__nv_bfloat16*>(C), ldc, M, N, K, act,
-      n_rows_w);
+      n_rows_w, gate, rows_per_img, imgs);
   TFIMM_LAUNCH_OK("gemm_bf16_skinny_kernel");
   return kOk;
 }

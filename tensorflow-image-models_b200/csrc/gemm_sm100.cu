@@ -42,14 +42,16 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 5 : 7);
   static constexpr int kSlabTotal = kNumEpiWarps * kSlabBytes;
-  static constexpr int kNumBarriers = 2 * kStages + 2 * kAccStages + kNumEpiWarps;
+  static constexpr int kNumBarriers = 3 * kStages + 2 * kAccStages + kNumEpiWarps;   // full, empty, ready (gated)
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kSlabTotal + kNumBarriers * 8 + 16 + 1024 /*alignment slack*/;
   static constexpr uint32_t kTmemCols = kAccStages * BLOCK_N;  // 512 / 256 / 128
 };
 
-template <int BLOCK_N, typename OutT>
-__global__ void __launch_bounds__(kNumThreads, 1)
+constexpr int kNumGateWarps = 4;   // gated instances only: one thread per A-tile row
+
+template <int BLOCK_N, typename OutT, bool kGated = false>
+__global__ void __launch_bounds__(kNumThreads + (kGated ? 32 * kNumGateWarps : 0), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c,
@@ -70,6 +72,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   auto tfull_bar = [&](int s) { return smem_bars + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return smem_bars + 8u * (2 * kStages + kAccStages + s); };
   auto res_bar = [&](int w) { return smem_bars + 8u * (2 * kStages + 2 * kAccStages + w); };
+  auto ready_bar = [&](int s) { return smem_bars + 8u * (2 * kStages + 2 * kAccStages + kNumEpiWarps + s); };
   const uint32_t tmem_ptr_smem = smem_bars + 8u * Cfg::kNumBarriers;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of smem_base
 
@@ -84,6 +87,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+      mbar_init(ready_bar(s), 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -147,7 +151,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(kGated ? ready_bar(stage) : full_bar(stage), phase);   // gated: the A tile has been rescaled
           tcgen05_fence_after();
           const uint64_t off = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
           const uint64_t da = da0 + off, db = db0 + off;
@@ -161,6 +165,78 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (kGated && warp_idx >= 2 + kNumEpiWarps) {
+    // ------------------------- A-operand gate (squeeze-excite) -------------------------
+    // Each of the four warps owns every fourth k-block (a whole 128 x 64 tile), so four stages are being rescaled at
+    // any time and the latency of one stage's chain (shared-memory loads -> multiply -> stores -> proxy fence -> arrive)
+    // is overlapped with the other three.  lane = one 16-byte chunk column (8 contraction indices) x 32 rows 4 apart:
+    // the gate values of a lane change only when its rows cross into the next image (two 16-byte loads, the first pair
+    // issued BEFORE the wait on the TMA barrier); a quarter-warp touches one whole 128-byte row (no bank conflicts
+    // under the 128B swizzle).  x * gate in fp32, back as bf16 -- the rounding of the separate scale pass
+    // (csrc/conv.cu, scale_channels_kernel) -- then the proxy fence that makes the generic-proxy writes visible to the
+    // tensor core's async-proxy reads, and one arrive on the stage's "ready" barrier.
+    const int wt = warp_idx - 2 - kNumEpiWarps;
+    const int c = lane & 7, r0 = lane >> 3;
+    auto load_gate = [&](int img, int k0, float4& ga, float4& gb) {
+      const float* g = p.a_scale + (long)img * p.K + k0;
+      ga = __ldg(reinterpret_cast<const float4*>(g));
+      gb = __ldg(reinterpret_cast<const float4*>(g + 4));
+    };
+    int stage = 0, turn = 0;   // stage / owner of the NEXT k-block in the CTA's global order
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / num_n_tiles;
+      const long row_first = (long)m_blk * kBlockM + r0;
+      long im0 = row_first / p.a_rows_per_img;
+      im0 = im0 < p.a_imgs ? im0 : p.a_imgs - 1;            // rows past M are zero-filled: any gate row will do
+      const int img0 = (int)im0;
+      const long bound0 = (im0 + 1) * p.a_rows_per_img - (long)m_blk * kBlockM;   // first tile row of the next image
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        if (turn == wt) {
+          const int k0 = kb * kBlockK + c * 8;
+          const bool valid = k0 < p.K;                       // K % 8 == 0: a chunk is inside or outside as a whole
+          float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+          if (valid) load_gate(img0, k0, ga, gb);
+          mbar_wait(full_bar(stage), phase);
+          if (valid) {
+            const uint32_t sa = smem_tiles + stage * Cfg::kStageBytes;
+            int cur = img0;
+            long bound = bound0;
+#pragma unroll 1
+            for (int b8 = 0; b8 < 4; ++b8) {
+              uint4 u[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 4 * (8 * b8 + i);
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(u[i].x), "=r"(u[i].y), "=r"(u[i].z), "=r"(u[i].w)
+                             : "r"(sa + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 4 * (8 * b8 + i);
+                if (r >= bound && cur < p.a_imgs - 1) {
+                  do { ++cur; bound += p.a_rows_per_img; } while (r >= bound && cur < p.a_imgs - 1);
+                  load_gate(cur, k0, ga, gb);
+                }
+                const float2 x0 = unpack_bf16x2(u[i].x), x1 = unpack_bf16x2(u[i].y), x2 = unpack_bf16x2(u[i].z),
+                             x3 = unpack_bf16x2(u[i].w);
+                const uint32_t o0 = pack_bf16x2(x0.x * ga.x, x0.y * ga.y), o1 = pack_bf16x2(x1.x * ga.z, x1.y * ga.w);
+                const uint32_t o2 = pack_bf16x2(x2.x * gb.x, x2.y * gb.y), o3 = pack_bf16x2(x3.x * gb.z, x3.y * gb.w);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))),
+                             "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                             : "memory");
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready_bar(stage));
+        }
+        turn = turn + 1 == kNumGateWarps ? 0 : turn + 1;
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -226,7 +302,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 // ------------------------------ host side -----------------------------------
-template <int BLOCK_N, typename OutT>
+template <int BLOCK_N, typename OutT, bool kGated = false>
 int launch_gemm(const void* A, int lda, const void* W, int ldw, const void* residual, int ldr, void* C, int ldc,
                 const GemmParams& p, cudaStream_t stream) {
   const int M = p.M, N = p.N, K = p.K;
@@ -243,14 +319,14 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, const void* resi
   } else {
     tr = tc;
   }
-  auto kernel = gemm_bf16_tcgen05_kernel<BLOCK_N, OutT>;
+  auto kernel = gemm_bf16_tcgen05_kernel<BLOCK_N, OutT, kGated>;
   static unsigned long long attr_devs = 0;  // per instantiation
   if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   }
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kernel<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, p);
+  kernel<<<grid, kNumThreads + (kGated ? 32 * kNumGateWarps : 0), Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, p);
   TFIMM_LAUNCH_OK("gemm_bf16_tcgen05_kernel");
   return kOk;
 }
@@ -339,7 +415,8 @@ bool prefer_pair(int M, int N) {
 }  // namespace
 
 int gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
-                     void* C, int ldc, int M, int N, int K, int act, cudaStream_t stream);
+                     void* C, int ldc, int M, int N, int K, int act, cudaStream_t stream, const float* gate = nullptr,
+                     int rows_per_img = 1, int imgs = 1);
 
 int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const float* bias,
                        const float* gamma, const void* residual, int ldr, void* C, int ldc, int M,
@@ -374,6 +451,31 @@ int gemm_bf16_dispatch(const void* A, int lda, const void* W, int ldw, const flo
       return kInvalidArgument;
   }
 #undef TFIMM_GEMM_CASE
+}
+
+// Dense layer whose input rows are first multiplied by a per-image channel gate (squeeze-excite): the projection
+// convolutions after SEModule (tfimm/layers/attention.py, efficientnet_blocks.py:241-248, 438-453).  bf16 out.
+int gemm_bf16_gated_dispatch(const void* A, int lda, const float* gate, int rows_per_img, int imgs, const void* W, int ldw,
+                             const float* bias, const void* residual, int ldr, void* C, int ldc, int M, int N, int K,
+                             int act, cudaStream_t stream) {
+  TFIMM_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 8 == 0, "gemm_gated: need K %% 8 == 0 (got M=%d N=%d K=%d)", M, N, K);
+  TFIMM_CHECK_ARG(gate != nullptr && rows_per_img > 0 && imgs > 0 && (reinterpret_cast<uintptr_t>(gate) & 15u) == 0,
+                  "gemm_gated: gate [imgs][K] fp32, 16-byte aligned");
+  TFIMM_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0, "gemm_gated: bias must be 16-byte aligned");
+  if (K <= 64) {   // short contraction: the streaming kernel scales its A fragments in registers
+    const int st = gemm_bf16_skinny(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, act, stream, gate, rows_per_img,
+                                    imgs);
+    if (st != kUnsupported) return st;
+  }
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.act = act; p.has_res = residual != nullptr ? 1 : 0;
+  p.a_scale = gate; p.a_rows_per_img = rows_per_img; p.a_imgs = imgs;
+  switch (pick_block_n(M, N)) {
+    case 256: return launch_gemm<256, __nv_bfloat16, true>(A, lda, W, ldw, residual, ldr, C, ldc, p, stream);
+    case 128: return launch_gemm<128, __nv_bfloat16, true>(A, lda, W, ldw, residual, ldr, C, ldc, p, stream);
+    default: return launch_gemm<64, __nv_bfloat16, true>(A, lda, W, ldw, residual, ldr, C, ldc, p, stream);
+  }
 }
 
 // k x k convolution (stride 1 or 2, symmetric padding (k-1)/2... given as `pad`) + bias + activation (+ residual),

@@ -157,8 +157,13 @@ class ConvNeXt(Model):
                     features[f"stage_{j}/downsample"] = xs.view(B, H, W, dim).clone()
             for k, blk in enumerate(st["blocks"]):
                 h = ops.dwconv_ln(xs.view(B, H, W, dim), blk["dw_w"], blk["dw_b"], *blk["n"], eps, adt)
-                hid = ops.gemm(h, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)
-                ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], gamma=blk["ls"], residual=xs, out=xs)
+                if adt == torch.bfloat16 and ops.mlp_fused_supported(dim, blk["fc1_w"].shape[0]):
+                    # one kernel: the (M, 4 dim) hidden activations stay in tensor memory (csrc/mlp_sm100.cu)
+                    ops.mlp_fused(h.view(-1, dim), blk["fc1_w"], blk["fc1_b"], blk["fc2_w"], blk["fc2_b"], c.act_layer,
+                                  gamma=blk["ls"], residual=xs, out=xs)
+                else:
+                    hid = ops.gemm(h, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)
+                    ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], gamma=blk["ls"], residual=xs, out=xs)
                 if return_features:
                     features[f"stage_{j}/block_{k}"] = xs.view(B, H, W, dim).clone()
         out = xs.view(B, H, W, -1)

@@ -315,8 +315,13 @@ class SwinTransformer(Model):
                 a = self._window_attention(qkv, blk, B, nw, n, heads, dh)
                 ops.gemm(a, blk["proj_w"], bias=blk["proj_b"], residual=xs, out=xs)
                 t = ops.layernorm(xs, *blk["n2"], eps, adt)
-                hid = ops.gemm(t, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)
-                ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], residual=xs, out=xs)
+                if adt == torch.bfloat16 and ops.mlp_fused_supported(dim, blk["fc1_w"].shape[0]):
+                    # one kernel: the (M, 4 dim) hidden activations stay in tensor memory (csrc/mlp_sm100.cu)
+                    ops.mlp_fused(t, blk["fc1_w"], blk["fc1_b"], blk["fc2_w"], blk["fc2_b"], c.act_layer, residual=xs,
+                                  out=xs)
+                else:
+                    hid = ops.gemm(t, blk["fc1_w"], bias=blk["fc1_b"], act=c.act_layer)
+                    ops.gemm(hid, blk["fc2_w"], bias=blk["fc2_b"], residual=xs, out=xs)
                 if return_features:
                     features[f"block_{block_idx}"] = xs.view(B, h * w, dim).clone()
                 block_idx += 1

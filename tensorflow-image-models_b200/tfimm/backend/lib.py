@@ -38,6 +38,8 @@ SIGNATURES = {
     "tfimm_b200_attention_f32": [_P, _P, _P, _P, _I, _L, _I, _I, _I, _F, _P, _P, _I, _P],
     "tfimm_b200_window_attention_bf16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "tfimm_b200_window_attention_tc_bf16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "tfimm_b200_gemm_bf16_gated": [_P, _I, _P, _I, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
+    "tfimm_b200_mlp_bf16": [_P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "tfimm_b200_patchify": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
     "tfimm_b200_assemble_tokens": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "tfimm_b200_cast": [_P, _I, _P, _I, _L, _P],

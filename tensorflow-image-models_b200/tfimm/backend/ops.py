@@ -70,7 +70,7 @@ def _call(name, *args, flops=0.0, nbytes=0.0):
         e0.record()
         _lib.check(fn(*args), name)
         e1.record()
-        trace.append((name.replace("tfimm_b200_", "").replace("conv_bf16", "gemm_bf16").replace("window_attention_tc_bf16", "window_attention_bf16"), e0, e1, float(flops),
+        trace.append((name.replace("tfimm_b200_", "").replace("conv_bf16", "gemm_bf16").replace("window_attention_tc_bf16", "window_attention_bf16").replace("gemm_bf16_gated", "gemm_bf16"), e0, e1, float(flops),
                       float(nbytes)))
     else:
         _lib.check(fn(*args), name)
@@ -117,6 +117,53 @@ def gemm(a, w, bias=None, act=None, gamma=None, residual=None, out=None, out_dty
         _call("tfimm_b200_gemm_f32", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
               _ptr(gamma), _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, act_code(act),
               int(bool(act_after_residual)), _stream(), flops=2.0 * M * N * K, nbytes=_nbytes(a, w, out, residual))
+    return out
+
+
+def gemm_gated(a, gate, rows_per_image, w, bias=None, act=None, residual=None):
+    """act((a * gate[row // rows_per_image]) @ w.T + bias) + residual, bf16: the squeeze-excite gate (B, K) fp32 is applied
+    to the A tile in shared memory (rounded to bf16 like ``scale_channels_``), not in a pass over HBM."""
+    _cuda(a, gate, w, bias, residual)
+    M, K = a.shape
+    N = w.shape[0]
+    assert a.dtype == w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K
+    assert gate.dtype == torch.float32 and gate.is_contiguous() and gate.shape[1] == K
+    assert gate.shape[0] * rows_per_image >= M
+    ldc = (N + 7) // 8 * 8
+    buf = torch.empty((M, ldc), device=a.device, dtype=torch.bfloat16)
+    out = buf[:, :N] if ldc != N else buf
+    if residual is not None:
+        assert residual.shape == (M, N) and residual.dtype == torch.bfloat16 and residual.stride(1) == 1
+    _call("tfimm_b200_gemm_bf16_gated", a.data_ptr(), a.stride(0), gate.data_ptr(), int(rows_per_image), gate.shape[0],
+          w.data_ptr(), w.stride(0), _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0,
+          out.data_ptr(), out.stride(0), M, N, K, act_code(act), _stream(), flops=2.0 * M * N * K,
+          nbytes=_nbytes(a, w, out, residual))
+    return out
+
+
+def mlp_fused_supported(C, hidden):
+    """Shapes of the fused fc1 -> act -> fc2 kernel (csrc/mlp_sm100.cu)."""
+    return C in (128, 256) and hidden % 128 == 0 and hidden >= 256
+
+
+def mlp_fused(a, w1, b1, w2, b2, act, gamma=None, residual=None, out=None):
+    """out = residual + gamma * (act(a @ w1.T + b1) @ w2.T + b2) in one kernel; the hidden activations stay on the SM.
+    a:(M,C) bf16, w1:(hidden,C), w2:(C,hidden) bf16, residual / out:(M,C) fp32 (may alias)."""
+    _cuda(a, w1, b1, w2, b2, gamma, residual, out)
+    M, C = a.shape
+    Hd = w1.shape[0]
+    assert w1.shape == (Hd, C) and w2.shape == (C, Hd), (a.shape, w1.shape, w2.shape)
+    assert a.dtype == w1.dtype == w2.dtype == torch.bfloat16
+    assert a.stride(1) == 1 and w1.stride(1) == 1 and w2.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, C), device=a.device, dtype=torch.float32)
+    assert out.shape == (M, C) and out.dtype == torch.float32 and out.stride(1) == 1
+    if residual is not None:
+        assert residual.shape == (M, C) and residual.dtype == torch.float32 and residual.stride(1) == 1
+    _call("tfimm_b200_mlp_bf16", a.data_ptr(), a.stride(0), w1.data_ptr(), w1.stride(0), _ptr(b1), w2.data_ptr(),
+          w2.stride(0), _ptr(b2), _ptr(gamma), _ptr(residual), residual.stride(0) if residual is not None else 0,
+          out.data_ptr(), out.stride(0), M, C, Hd, act_code(act), _stream(), flops=4.0 * M * C * Hd,
+          nbytes=_nbytes(a, w1, w2, out, residual))
     return out
 
 

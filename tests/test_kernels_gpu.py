@@ -732,3 +732,81 @@ def test_gemm_short_contraction_streaming_kernel(M, K, N, act):
     torch.cuda.synchronize()
     assert (out_r.float() - ref_r).abs().max().item() <= 2.0 ** -7 * ref_r.abs().max().item() + 1e-5
     assert torch.equal(out_r, buf)
+
+
+@pytest.mark.parametrize("M,C,mult", [(256, 128, 4), (1000, 128, 4), (37 * 256 + 13, 128, 4), (150 * 256, 128, 4),
+                                      (512, 256, 4), (777, 256, 4), (90 * 256 + 5, 256, 4), (3000, 128, 2),
+                                      (2048, 256, 3)])
+@pytest.mark.parametrize("act,with_gamma", [("gelu", True), ("gelu", False), ("swish", False)])
+def test_mlp_fused_equals_two_gemms(M, C, mult, act, with_gamma):
+    """fc1 -> act -> fc2 -> * gamma -> + residual in one kernel (csrc/mlp_sm100.cu): same rounding points as the
+    two-GEMM form (bf16 hidden, fp32 accumulation in ascending k), so the two agree to fp32 summation noise."""
+    ops = _ops()
+    Hd = mult * C
+    g = torch.Generator(device="cuda").manual_seed(M + C + Hd)
+    a_full = torch.randn(M, C + 8, device="cuda", generator=g).to(torch.bfloat16)
+    a = a_full[:, :C]                                   # lda != C
+    w1 = (torch.randn(Hd, C, device="cuda", generator=g) / C ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(C, Hd, device="cuda", generator=g) / Hd ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn(Hd, device="cuda", generator=g)
+    b2 = torch.randn(C, device="cuda", generator=g)
+    gamma = torch.randn(C, device="cuda", generator=g) if with_gamma else None
+    res = torch.randn(M, C, device="cuda", generator=g)
+    out = ops.mlp_fused(a, w1, b1, w2, b2, act, gamma=gamma, residual=res)
+    buf = res.clone()
+    ops.mlp_fused(a, w1, b1, w2, b2, act, gamma=gamma, residual=buf, out=buf)     # in place
+    plain = ops.mlp_fused(a, w1, b1, w2, b2, act, gamma=gamma)                    # no residual
+    hid = ops.gemm(a, w1, bias=b1, act=act)
+    two = ops.gemm(hid, w2, bias=b2, gamma=gamma, residual=res, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    from oracle import emulate_bf16
+    ref = emulate_bf16.mlp_fused(a, w1, b1, w2, b2, act, gamma=gamma, residual=res).double()
+    scale = ref.abs().max().item()
+    assert out.shape == (M, C) and out.dtype == torch.float32
+    assert torch.equal(out, buf)
+    assert (plain.double() - (ref - res.double())).abs().max().item() <= 3e-3 * scale
+    # against the two kernels: identical hidden roundings up to the rare flip caused by fp32 summation order
+    assert (out - two).abs().max().item() <= 2e-3 * scale
+    assert ((out - two).abs() > 1e-5 * scale).float().mean().item() < 5e-2
+    # against exact arithmetic with the same storage points
+    assert (out.double() - ref).abs().max().item() <= 3e-3 * scale
+    assert (out.double() - ref).pow(2).mean().sqrt().item() <= 2e-4 * scale
+
+
+def test_mlp_fused_rejects_other_shapes():
+    ops = _ops()
+    assert not ops.mlp_fused_supported(96, 384) and not ops.mlp_fused_supported(512, 2048)
+    assert ops.mlp_fused_supported(128, 512) and ops.mlp_fused_supported(256, 1024)
+    a = torch.zeros(256, 512, device="cuda", dtype=torch.bfloat16)
+    w1 = torch.zeros(2048, 512, device="cuda", dtype=torch.bfloat16)
+    w2 = torch.zeros(512, 2048, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(Exception, match="mlp_fused"):
+        ops.mlp_fused(a, w1, None, w2, None, "gelu")
+
+
+@pytest.mark.parametrize("B,HW,K,N", [(3, 9025, 144, 32), (4, 2304, 192, 32), (2, 576, 336, 56), (5, 144, 1632, 272),
+                                      (7, 130, 48, 24), (2, 100, 960, 160), (3, 36, 2688, 448), (3, 9025, 48, 24),
+                                      (2, 36100, 32, 16), (5, 1000, 56, 336)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_gemm_gated_equals_scale_then_gemm(B, HW, K, N, with_res):
+    """Squeeze-excite gate applied to the A tile in shared memory (tcgen05 kernel) or to the A fragments in registers
+    (K <= 64: streaming kernel): the products scale_channels_ would have written, then the same GEMM."""
+    ops = _ops()
+    M = B * HW
+    g = torch.Generator(device="cuda").manual_seed(B + HW + K + N)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    gate = torch.sigmoid(torch.randn(B, K, device="cuda", generator=g))
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16) if with_res else None
+    out = ops.gemm_gated(a, gate, HW, w, bias=bias, residual=res)
+    scaled = ops.scale_channels_(a.clone().view(B, HW, K), gate).view(M, K)
+    want = ops.gemm(scaled, w, bias=bias, residual=res, block_n=64)
+    torch.cuda.synchronize()
+    from oracle import emulate_bf16
+    ref = emulate_bf16.gemm_gated(a, gate, HW, w, bias=bias, residual=res).float()
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16
+    assert (out.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-5
+    # same products, same k order: only the tile width (accumulation grouping inside the tensor core) may differ
+    assert (out != want).float().mean().item() < 1e-2
+    assert (out.float() - want.float()).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-5
