@@ -288,10 +288,14 @@ def global_avg_pool(x):
     return x.to(_HP).reshape(B, -1, C).mean(dim=1)
 
 
-def im2col(x, ks, stride, padding, out_dtype, groups=1):
+def im2col(x, ks, stride, padding, out_dtype, groups=1, pre=None):
     B, H, W, C = x.shape
     Ho, Wo, pads = _pads(H, W, ks, stride, padding)
-    xin = F.pad(x.to(_HP).permute(0, 3, 1, 2), pads)
+    xh = x.to(_HP)
+    if pre is not None:   # raw pixels: create_preprocessing before the (zero) padding
+        mean, inv_std, scale = pre
+        xh = (xh * scale - mean.to(_HP)) * inv_std.to(_HP)
+    xin = F.pad(xh.permute(0, 3, 1, 2), pads)
     cols = F.unfold(xin, ks, stride=stride)  # (B, C*ks*ks, L), rows ordered (c, ky, kx)
     cols = cols.view(B, C, ks * ks, Ho * Wo).permute(0, 3, 2, 1)  # (B, L, (ky,kx), c)
     cg = C // groups

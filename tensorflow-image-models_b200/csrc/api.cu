@@ -75,7 +75,8 @@ int dwconv_ln(const void*, int, const float*, const float*, const float*, const 
 int dwconv_bias_act(const void*, int, const float*, const float*, void*, float*, int, int, int, int, int, int,
                     int, int, int, int, int, cudaStream_t);
 int global_avg_pool(const void*, int, float*, int, int, int, cudaStream_t);
-int im2col(const void*, int, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int im2col(const void*, int, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t, float,
+           const float*, const float*);
 int group_norm(const void*, int, const float*, const float*, const void*, void*, float*, int, int, int, int, float, int,
                cudaStream_t);
 int blur_pool(const void*, int, void*, int, int, int, int, int, int, int, cudaStream_t);
@@ -215,7 +216,14 @@ int tfimm_b200_global_avg_pool(const void* x, int dtype, float* out, int B, int 
 int tfimm_b200_im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int groups,
                       int ks, int stride, int pad_t, int pad_l, int Ho, int Wo, int Kpad, void* stream) {
   return tfimm::im2col(x, in_dtype, out, out_dtype, B, H, W, C, groups, ks, stride, pad_t, pad_l, Ho, Wo, Kpad,
-                       S(stream));
+                       S(stream), 1.0f, nullptr, nullptr);
+}
+
+int tfimm_b200_im2col_u8(const void* x, void* out, int out_dtype, int B, int H, int W, int C, int ks, int stride,
+                         int pad_t, int pad_l, int Ho, int Wo, int Kpad, float scale, const float* mean,
+                         const float* inv_std, void* stream) {
+  return tfimm::im2col(x, tfimm::kU8, out, out_dtype, B, H, W, C, 1, ks, stride, pad_t, pad_l, Ho, Wo, Kpad, S(stream),
+                       scale, mean, inv_std);
 }
 
 int tfimm_b200_group_norm(const void* x, int dtype, const float* gamma, const float* beta, const void* residual,

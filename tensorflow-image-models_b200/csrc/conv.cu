@@ -270,9 +270,14 @@ __global__ void global_avg_pool_kernel(const T* __restrict__ x, float* __restric
 // flattened.  G > 1 lays the groups of a grouped convolution out as G separate [M][Kpad] matrices, one GEMM each.
 // KS_T / C_T: compile-time kernel size and channel count for the RGB stems (7x7 and 3x3 on 3 channels), where the
 // per-element (tap, channel) decomposition would otherwise be runtime integer divisions; 0 = runtime values.
+// pre_mean != null (raw uint8 pixels): every in-bounds value becomes (v * pre_scale - mean[c]) * inv_std[c] -- the
+// reference's create_preprocessing (tfimm/models/factory.py:153-169) -- while the zero padding stays zero, as when the
+// convolution pads the preprocessed image.
 template <typename InT, typename OutT, int KS_T = 0, int C_T = 0>
 __global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out, int B, int H, int W, int C_rt, int G,
-                              int Ho, int Wo, int ks_rt, int stride, int pad_t, int pad_l, int Kpad) {
+                              int Ho, int Wo, int ks_rt, int stride, int pad_t, int pad_l, int Kpad,
+                              float pre_scale = 1.f, const float* __restrict__ pre_mean = nullptr,
+                              const float* __restrict__ pre_inv_std = nullptr) {
   const int C = C_T > 0 ? C_T : C_rt;
   const int ks = KS_T > 0 ? KS_T : ks_rt;
   const int cg = C_T > 0 ? C_T : C / G;
@@ -299,6 +304,11 @@ __global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out,
       const int iy = oy * stride + ky - pad_t, ix = ox * stride + kx - pad_l;
       if (k0 < K && iy >= 0 && iy < H && ix >= 0 && ix < W) {
         ld8(x + ((b * H + iy) * W + ix) * (long)C + coff + c, v);
+        if (pre_mean != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[j] = (v[j] * pre_scale - __ldg(pre_mean + coff + c + j)) * __ldg(pre_inv_std + coff + c + j);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -312,8 +322,10 @@ __global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out,
           const int tap = k / cg, c = k % cg;
           const int ky = tap / ks, kx = tap % ks;
           const int iy = oy * stride + ky - pad_t, ix = ox * stride + kx - pad_l;
-          if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
             val = ld_as_float(x + ((b * H + iy) * W + ix) * (long)C + coff + c);
+            if (pre_mean != nullptr) val = (val * pre_scale - __ldg(pre_mean + coff + c)) * __ldg(pre_inv_std + coff + c);
+          }
         }
         v[j] = val;
       }
@@ -330,7 +342,8 @@ __global__ void im2col_kernel(const InT* __restrict__ x, OutT* __restrict__ out,
 template <typename InT>
 __global__ void __launch_bounds__(256)
 im2col_stem7_kernel(const InT* __restrict__ x, __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo,
-                    int pad_t, int pad_l, int Kpad) {
+                    int pad_t, int pad_l, int Kpad, float pre_scale = 1.f, const float* __restrict__ pre_mean = nullptr,
+                    const float* __restrict__ pre_inv_std = nullptr) {
   constexpr int TW = 32;                  // output pixels per CTA
   constexpr int ROW = ((TW - 1) * 2 + 7) * 3;  // 207 input values per tap row
   __shared__ __nv_bfloat16 tile[7][ROW + 1];
@@ -346,7 +359,10 @@ im2col_stem7_kernel(const InT* __restrict__ x, __nv_bfloat16* __restrict__ out, 
     const int r = idx / ROW, e = idx - r * ROW;
     const int iy = iy0 + r, ge = e0 + e;
     float v = 0.f;
-    if (iy >= 0 && iy < H && ge >= 0 && ge < W * 3) v = ld_as_float(x + ((long)b * H + iy) * W * 3 + ge);
+    if (iy >= 0 && iy < H && ge >= 0 && ge < W * 3) {
+      v = ld_as_float(x + ((long)b * H + iy) * W * 3 + ge);
+      if (pre_mean != nullptr) v = (v * pre_scale - __ldg(pre_mean + ge % 3)) * __ldg(pre_inv_std + ge % 3);
+    }
     tile[r][e] = __float2bfloat16_rn(v);
   }
   __syncthreads();
@@ -506,13 +522,42 @@ inline unsigned conv_grid_for(long total, int threads) {
 }  // namespace
 
 int im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, int W, int C, int groups, int ks,
-           int stride, int pad_t, int pad_l, int Ho, int Wo, int Kpad, cudaStream_t stream) {
+           int stride, int pad_t, int pad_l, int Ho, int Wo, int Kpad, cudaStream_t stream, float pre_scale,
+           const float* pre_mean, const float* pre_inv_std) {
   TFIMM_CHECK_ARG(B > 0 && ks > 0 && stride > 0 && Ho > 0 && Wo > 0, "im2col: bad geometry");
   TFIMM_CHECK_ARG(groups > 0 && C % groups == 0, "im2col: C must be divisible by groups (C=%d groups=%d)", C, groups);
   TFIMM_CHECK_ARG(Kpad % 8 == 0 && Kpad >= ks * ks * (C / groups),
                   "im2col: Kpad must be a multiple of 8 and >= k*k*C/groups");
+  TFIMM_CHECK_ARG((pre_mean == nullptr) == (pre_inv_std == nullptr), "im2col: mean and inv_std come together");
+  TFIMM_CHECK_ARG((in_dtype == kU8) == (pre_mean != nullptr), "im2col: uint8 input <=> fused preprocessing");
   const long total = (long)B * Ho * Wo * (Kpad / 8) * groups;
   const unsigned grid = conv_grid_for(total, 256);
+  if (in_dtype == kU8) {
+    // raw pixels (stems): (v * scale - mean[c]) / std[c] inside the gather
+    const uint8_t* xu = reinterpret_cast<const uint8_t*>(x);
+    if (C == 3 && groups == 1 && ks == 7 && stride == 2 && out_dtype == kBF16 && Kpad >= 147) {
+      const long ctas = (long)B * Ho * ((Wo + 31) / 32);
+      im2col_stem7_kernel<<<(unsigned)ctas, 256, 0, stream>>>(xu, reinterpret_cast<__nv_bfloat16*>(out), H, W, Ho, Wo, pad_t,
+                                                           pad_l, Kpad, pre_scale, pre_mean, pre_inv_std);
+    } else if (C == 3 && groups == 1 && ks == 3 && out_dtype == kBF16) {
+      im2col_kernel<uint8_t, __nv_bfloat16, 3, 3><<<grid, 256, 0, stream>>>(
+          xu, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, groups, Ho, Wo, ks, stride, pad_t, pad_l, Kpad, pre_scale,
+          pre_mean, pre_inv_std);
+    } else if (out_dtype == kBF16) {
+      im2col_kernel<uint8_t, __nv_bfloat16><<<grid, 256, 0, stream>>>(xu, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
+                                                                     groups, Ho, Wo, ks, stride, pad_t, pad_l, Kpad,
+                                                                     pre_scale, pre_mean, pre_inv_std);
+    } else if (out_dtype == kF32) {
+      im2col_kernel<uint8_t, float><<<grid, 256, 0, stream>>>(xu, reinterpret_cast<float*>(out), B, H, W, C, groups, Ho, Wo,
+                                                             ks, stride, pad_t, pad_l, Kpad, pre_scale, pre_mean,
+                                                             pre_inv_std);
+    } else {
+      set_last_error("im2col: unsupported output dtype %d", out_dtype);
+      return kInvalidArgument;
+    }
+    TFIMM_LAUNCH_OK("im2col_kernel (uint8)");
+    return kOk;
+  }
 #define TFIMM_I2C(IN, OUT)                                                                              \
   im2col_kernel<IN, OUT><<<grid, 256, 0, stream>>>(reinterpret_cast<const IN*>(x), reinterpret_cast<OUT*>(out), \
                                                   B, H, W, C, groups, Ho, Wo, ks, stride, pad_t, pad_l, Kpad)

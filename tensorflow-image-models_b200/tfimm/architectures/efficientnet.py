@@ -170,6 +170,7 @@ def resolve_blocks(cfg: EfficientNetConfig) -> List[BlockSpec]:
 
 class EfficientNet(Model):
     cfg_class = EfficientNetConfig
+    accepts_uint8 = True   # raw pixels: create_preprocessing fused into the stem's im2col gather
 
     def __init__(self, cfg: EfficientNetConfig, *args, **kwargs):
         if isinstance(cfg, dict):
@@ -310,7 +311,9 @@ class EfficientNet(Model):
         if k == 1 and stride == 1:
             cols, Ho, Wo = x.reshape(-1, x.shape[-1]), x.shape[1], x.shape[2]
         else:
-            cols, Ho, Wo = ops.im2col(x, k, stride, self.cfg.padding, self.act_dtype)
+            # raw uint8 pixels (stem): create_preprocessing is fused into the gather
+            pre = self._pixel_stats(x.device) if x.dtype == torch.uint8 else None
+            cols, Ho, Wo = ops.im2col(x, k, stride, self.cfg.padding, self.act_dtype, pre=pre)
         res2d = residual.reshape(-1, residual.shape[-1]) if residual is not None else None
         if gate is not None:
             y = ops.gemm_gated(cols, gate, Ho * Wo, w, bias=bias, act=act, residual=res2d)

@@ -130,6 +130,7 @@ def resolve_blocks(cfg: ResNetConfig) -> List[_Block]:
 
 class ResNet(Model):
     cfg_class = ResNetConfig
+    accepts_uint8 = True   # raw pixels: create_preprocessing fused into the stem's im2col gather
     keys_to_ignore_on_load_missing = ["blur_kernel"]
 
     def __init__(self, cfg: ResNetConfig, *args, **kwargs):
@@ -303,7 +304,9 @@ class ResNet(Model):
         if k == 1 and stride == 1:
             cols, Ho, Wo = x.reshape(-1, x.shape[-1]), x.shape[1], x.shape[2]
         else:
-            cols, Ho, Wo = ops.im2col(x, k, stride, pad, self.act_dtype)
+            # raw uint8 pixels (first stem conv): create_preprocessing is fused into the gather
+            pre = self._pixel_stats(x.device) if x.dtype == torch.uint8 else None
+            cols, Ho, Wo = ops.im2col(x, k, stride, pad, self.act_dtype, pre=pre)
         if gn is not None:
             # conv -> GroupNorm (-> + shortcut) -> act: the norm needs the whole (H, W, C/G) extent, so it cannot be
             # an epilogue of the GEMM tile; residual and activation ride on the normalisation pass instead

@@ -47,6 +47,7 @@ SIGNATURES = {
     "tfimm_b200_dwconv_bias_act": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "tfimm_b200_global_avg_pool": [_P, _I, _P, _I, _I, _I, _P],
     "tfimm_b200_im2col": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "tfimm_b200_im2col_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
     "tfimm_b200_group_norm": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
     "tfimm_b200_blur_pool": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "tfimm_b200_se_gate": [_P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

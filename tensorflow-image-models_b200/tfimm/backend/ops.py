@@ -70,7 +70,7 @@ def _call(name, *args, flops=0.0, nbytes=0.0):
         e0.record()
         _lib.check(fn(*args), name)
         e1.record()
-        trace.append((name.replace("tfimm_b200_", "").replace("conv_bf16", "gemm_bf16").replace("window_attention_tc_bf16", "window_attention_bf16").replace("gemm_bf16_gated", "gemm_bf16"), e0, e1, float(flops),
+        trace.append((name.replace("tfimm_b200_", "").replace("conv_bf16", "gemm_bf16").replace("window_attention_tc_bf16", "window_attention_bf16").replace("gemm_bf16_gated", "gemm_bf16").replace("im2col_u8", "im2col"), e0, e1, float(flops),
                       float(nbytes)))
     else:
         _lib.check(fn(*args), name)
@@ -390,9 +390,10 @@ def conv_geometry(H, W, ks, stride, padding):
     return (H + 2 * pd - ks) // stride + 1, (W + 2 * pd - ks) // stride + 1, pd, pd
 
 
-def im2col(x, ks, stride, padding, out_dtype, groups=1):
+def im2col(x, ks, stride, padding, out_dtype, groups=1, pre=None):
     """x: (B,H,W,C) -> ((B*Ho*Wo, ceil8(ks*ks*C)), Ho, Wo); groups > 1: ((groups, B*Ho*Wo, ceil8(ks*ks*C/groups)), ...)
-    with one im2col matrix per channel group."""
+    with one im2col matrix per channel group.  uint8 ``x`` (raw pixels) needs ``pre = (mean, inv_std, scale)``: the
+    gathered values are (x * scale - mean[c]) * inv_std[c], the padding stays zero."""
     _cuda(x)
     B, H, W, C = x.shape
     assert x.is_contiguous() and C % groups == 0
@@ -400,6 +401,13 @@ def im2col(x, ks, stride, padding, out_dtype, groups=1):
     Kpad = (ks * ks * (C // groups) + 7) // 8 * 8
     shape = (B * Ho * Wo, Kpad) if groups == 1 else (groups, B * Ho * Wo, Kpad)
     out = torch.empty(shape, device=x.device, dtype=out_dtype)
+    if x.dtype == torch.uint8:
+        assert pre is not None and groups == 1, "uint8 input: pass pre=(mean, inv_std, scale)"
+        mean, inv_std, scale = pre
+        _cuda(mean, inv_std)
+        _call("tfimm_b200_im2col_u8", x.data_ptr(), out.data_ptr(), _code(out), B, H, W, C, ks, stride, pt, pl, Ho, Wo,
+              Kpad, float(scale), mean.data_ptr(), inv_std.data_ptr(), _stream(), nbytes=_nbytes(x, out))
+        return out, Ho, Wo
     _call("tfimm_b200_im2col", x.data_ptr(), _code(x), out.data_ptr(), _code(out), B, H, W, C, groups, ks, stride,
           pt, pl, Ho, Wo, Kpad, _stream(), nbytes=_nbytes(x, out))
     return out, Ho, Wo

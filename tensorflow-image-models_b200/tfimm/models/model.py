@@ -219,7 +219,7 @@ class Model:
             # (reference tfimm/models/factory.py:153-169); see _patchify.
             if not self.accepts_uint8:
                 raise TypeError(f"{type(self).__name__} takes preprocessed float images "
-                                "(fused uint8 preprocessing is implemented for the patchify families).")
+                                "(fused uint8 preprocessing is implemented for the patchify and conv-stem families).")
             return x.to(self.device, non_blocking=True).contiguous()
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
@@ -235,15 +235,20 @@ class Model:
 
         if x.dtype != torch.uint8:
             return ops.patchify(x, patch_size, self.act_dtype)
-        if getattr(self, "_pre_stats", None) is None or self._pre_stats[0].device != x.device:
+        mean, inv_std, scale = self._pixel_stats(x.device)
+        return ops.patchify(x, patch_size, self.act_dtype, mean=mean, inv_std=inv_std, scale=scale)
+
+    def _pixel_stats(self, device):
+        """(mean, 1 / std, 1 / 255) of create_preprocessing (reference tfimm/models/factory.py:153-169) as device
+        tensors, for the kernels that take raw uint8 pixels (patchify, the im2col of the convolutional stems)."""
+        if getattr(self, "_pre_stats", None) is None or self._pre_stats[0].device != device:
             n = self.cfg.in_channels
 
             def cyc(v):
-                return torch.tensor((list(v) * (n // len(v) + 1))[:n], dtype=torch.float32, device=x.device)
+                return torch.tensor((list(v) * (n // len(v) + 1))[:n], dtype=torch.float32, device=device)
 
             self._pre_stats = (cyc(self.cfg.mean), 1.0 / cyc(self.cfg.std))
-        mean, inv_std = self._pre_stats
-        return ops.patchify(x, patch_size, self.act_dtype, mean=mean, inv_std=inv_std, scale=1.0 / 255.0)
+        return self._pre_stats[0], self._pre_stats[1], 1.0 / 255.0
 
     # ------------------------------------------------------------------ public forward API
     @property

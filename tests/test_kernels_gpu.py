@@ -810,3 +810,28 @@ def test_gemm_gated_equals_scale_then_gemm(B, HW, K, N, with_res):
     # same products, same k order: only the tile width (accumulation grouping inside the tensor core) may differ
     assert (out != want).float().mean().item() < 1e-2
     assert (out.float() - want.float()).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-5
+
+
+@pytest.mark.parametrize("C,ks,stride,padding,H,W", [(3, 7, 2, 3, 64, 80), (3, 3, 2, "same", 45, 38), (3, 3, 2, 1, 40, 40),
+                                                     (1, 3, 2, "same", 33, 33), (6, 7, 2, 3, 32, 32), (8, 3, 1, 1, 20, 24)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_im2col_uint8_fuses_preprocessing(C, ks, stride, padding, H, W, out_dtype):
+    """Raw uint8 pixels: the gather applies (x / 255 - mean) / std per channel and keeps the padding at zero -- the same
+    matrix as im2col of the preprocessed fp32 image."""
+    ops = _ops()
+    B = 3
+    g = torch.Generator(device="cuda").manual_seed(C * 100 + ks)
+    raw = torch.randint(0, 256, (B, H, W, C), device="cuda", generator=g, dtype=torch.uint8)
+    mean = torch.rand(C, device="cuda", generator=g)
+    inv_std = 1.0 / (0.2 + torch.rand(C, device="cuda", generator=g))
+    cols, Ho, Wo = ops.im2col(raw, ks, stride, padding, out_dtype, pre=(mean, inv_std, 1.0 / 255.0))
+    pre = ((raw.float() * (1.0 / 255.0) - mean) * inv_std).contiguous()
+    want, Ho2, Wo2 = ops.im2col(pre, ks, stride, padding, out_dtype)
+    torch.cuda.synchronize()
+    assert (Ho, Wo) == (Ho2, Wo2) and cols.shape == want.shape
+    if out_dtype == torch.bfloat16:
+        assert (cols != want).float().mean().item() < 2e-3          # an fma contraction may flip a rare rounding
+        assert (cols.float() - want.float()).abs().max().item() <= 2.0 ** -7 * want.float().abs().max().item()
+    else:
+        assert torch.allclose(cols, want, rtol=2e-6, atol=2e-6)     # x * scale - mean: fma in the kernel, two ops in torch
+    assert torch.equal(cols == 0, want == 0)                        # the padding stays exactly zero

@@ -302,7 +302,8 @@ def test_cuda_graph_replay_matches_eager():
 
 
 @pytest.mark.parametrize("name,family", [("vit_tiny_patch16_224", "vit"), ("convnext_tiny", "convnext"),
-                                         ("swin_tiny_patch4_window7_224", "swin")])
+                                         ("swin_tiny_patch4_window7_224", "swin"), ("efficientnet_b0", "efficientnet"),
+                                         ("resnet18", "resnet"), ("resnet26d", "resnet")])
 def test_fused_uint8_preprocessing_equals_create_preprocessing(name, family):
     """model(uint8 pixels) == model(create_preprocessing(name)(pixels))  (reference factory.py:153-169)."""
     import importlib
@@ -320,6 +321,12 @@ def test_fused_uint8_preprocessing_equals_create_preprocessing(name, family):
     a = model(torch.from_numpy(raw).cuda())
     b = model(torch.from_numpy(pre(raw)).cuda())
     assert _nerr(a, b)[0] < 1e-5
+    # bf16 engine: the stem sees bf16((x / 255 - mean) / std) either way
+    m16 = tfimm.create_model(name, precision="bf16", device="cuda")
+    m16.load_weights_dict(params.random_params(omod.param_shapes(m16.cfg), seed=21))
+    a16 = m16(torch.from_numpy(raw).cuda())
+    b16 = m16(torch.from_numpy(pre(raw)).cuda())
+    assert _nerr(a16, b16)[0] < 2e-3
 
 
 def test_inference_pipeline_matches_direct_calls():
