@@ -21,7 +21,8 @@ ROOT = Path(__file__).resolve().parent.parent
 
 # kernel-name substring -> family name used by tfimm.backend.ops._call / bench.py
 FAMILIES = [
-    ("gemm_bf16_tcgen05", "gemm_bf16"), ("gemm_f32", "gemm_f32"),
+    ("mlp_fused", "mlp_bf16"), ("gemm_bf16_tcgen05", "gemm_bf16"), ("gemm_bf16_skinny", "gemm_bf16"),
+    ("gemm_f32", "gemm_f32"),
     ("vit_attention", "attention_bf16"), ("attention_cls", "attention_cls_bf16"), ("attention_f32", "attention_f32"),
     ("window_attention", "window_attention_bf16"),
     ("layernorm_patch2x2", "layernorm_patch2x2"), ("patch_merge_ln", "patch_merge_ln"), ("layernorm", "layernorm"),
@@ -94,6 +95,21 @@ def parse(paths):
                        "ncu_ms": {k: round(v["ns"] / 1e6, 4) for k, v in fam.items()},
                        "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one eager "
                               "forward (cold-cache, serialised launches)"}
+        # per-kernel launch list of the same pass (cold-cache, serialised: compare SHARES with the bench line, not times)
+        kern = {}
+        for d in per.values():
+            k = kern.setdefault(re.sub(r"\(.*", "", d["kernel"])[-72:], {"n": 0, "ns": 0.0, "bytes": 0.0})
+            k["n"] += 1
+            k["ns"] += d["ns"]
+            k["bytes"] += d["bytes"]
+        tot_ns = sum(k["ns"] for k in kern.values()) or 1.0
+        lines_out = [f"# {name}, batch {batch}: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,"
+                     "gpu__time_duration.sum --clock-control none, one eager forward",
+                     "# kernel | launches | avg us | share of the pass | DRAM MB per launch"]
+        for kname, k in sorted(kern.items(), key=lambda kv: -kv[1]["ns"]):
+            lines_out.append(f"{kname:74s} {k['n']:4d} {k['ns'] / k['n'] / 1e3:9.1f} {100 * k['ns'] / tot_ns:6.1f}% "
+                             f"{k['bytes'] / k['n'] / 1e6:9.1f}")
+        (ROOT / "profiles" / f"r02_launches_{name}.txt").write_text("\n".join(lines_out) + "\n")
         tot = sum(v["bytes"] for v in fam.values())
         print(f"{name} (batch {batch}): {tot / 1e9:.2f} GB DRAM traffic per forward = {tot / batch / 1e6:.1f} MB/image")
         for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["bytes"]):
