@@ -75,7 +75,7 @@ int tfimm_b200_gemm_bf16_gated(const void* A, int lda, const float* gate, int ro
 
 /* Fused MLP block of the narrow stages:  out = residual + gamma * (act(A @ W1^T + b1) @ W2^T + b2).
  * A:[M,C] bf16 (the normalised activations), W1:[hidden,C] bf16, W2:[C,hidden] bf16, b1:[hidden], b2:[C], gamma:[C] or
- * NULL (ConvNeXt layer scale), residual / out:[M,C] fp32 (residual may alias out, or be NULL).  C in {128, 256},
+ * NULL (ConvNeXt layer scale), residual / out:[M,C] fp32 (residual may alias out, or be NULL).  C in {96, 128, 192, 256},
  * hidden a multiple of 128: other shapes return TFIMM_B200_UNSUPPORTED and the caller runs two tfimm_b200_gemm_bf16.
  * One CTA pair per 256 rows walks the hidden dimension in chunks of 128: fc1 chunk (tcgen05, cta_group::2) ->
  * bias + activation -> bf16 back into tensor memory -> A operand of the fc2 chunk product; the [M,hidden]

@@ -95,7 +95,7 @@ def gemm_gated(a, gate, rows_per_image, w, bias=None, act=None, residual=None):
 
 
 def mlp_fused_supported(C, hidden):
-    return C in (128, 256) and hidden % 128 == 0 and hidden >= 256
+    return C in (96, 128, 192, 256) and hidden % 128 == 0 and hidden >= 256
 
 
 def mlp_fused(a, w1, b1, w2, b2, act, gamma=None, residual=None, out=None):

@@ -1,4 +1,4 @@
-// Fused MLP block for narrow stages (C = 128 or 256 channels):
+// Fused MLP block for narrow stages (C = 96, 128, 192 or 256 channels):
 //
 //     out[M,C] = residual[M,C] + gamma[C] * ( act(A[M,C] @ W1[H,C]^T + b1[H]) @ W2[C,H]^T + b2[C] )
 //
@@ -35,13 +35,13 @@ constexpr int kMlpThreads = 32 * (2 + kMlpHidWarps);
 
 template <int C>
 struct MlpCfg {
-  static constexpr int kKB1 = C / 64;                        // k-blocks of fc1
-  static constexpr int kABytes = kKB1 * kMlpRows * 128;      // one A tile: 32 / 64 KB
-  static constexpr int kABufs = C == 128 ? 2 : 1;
-  static constexpr int kW1Bytes = kKB1 * (kHC / 2) * 128;    // this CTA's 64 rows of a W1 chunk: 16 / 32 KB
-  static constexpr int kW2Bytes = 2 * (C / 2) * 128;         // this CTA's C/2 rows of a W2 chunk (2 k-blocks): 16 / 32 KB
-  static constexpr int kWStages = C == 128 ? 3 : 2;
-  static constexpr int kOutWarps = C == 128 ? 16 : 8;        // warps that also drain D2
+  static constexpr int kKB1 = (C + 63) / 64;                 // k-blocks of fc1 (C = 96: the second one is half TMA zero fill)
+  static constexpr int kABytes = kKB1 * kMlpRows * 128;      // one A tile: 32 / 48 / 64 KB
+  static constexpr int kABufs = C <= 128 ? 2 : 1;
+  static constexpr int kW1Bytes = kKB1 * (kHC / 2) * 128;    // this CTA's 64 rows of a W1 chunk: 16 / 24 / 32 KB
+  static constexpr int kW2Bytes = 2 * (C / 2) * 128;         // this CTA's C/2 rows of a W2 chunk (2 k-blocks): 12 .. 32 KB
+  static constexpr int kWStages = C <= 192 ? 3 : 2;
+  static constexpr int kOutWarps = C == 128 ? 16 : (C == 96 ? 12 : 8);   // warps that also drain D2 (C / 32 chunks x 4)
   static constexpr int kOutGroups = kOutWarps / 4;
   static constexpr int kSlabTotal = kOutWarps * kEpiSlabBytes;
   static constexpr int kNumBars = 2 * kABufs + 4 * kWStages + 2 + 2 + 2 + kMlpHidWarps;
@@ -49,7 +49,8 @@ struct MlpCfg {
       kABufs * kABytes + kWStages * (kW1Bytes + kW2Bytes) + kSlabTotal + kNumBars * 8 + 16 + 1024;
   static constexpr uint32_t kD2Col = 256;                    // D1/H buffers at columns 0 and 128, D2 from 256
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
-  static_assert(C == 128 || C == 256, "fused MLP: 128 or 256 channels");
+  static_assert(C == 96 || C == 128 || C == 192 || C == 256, "fused MLP: 96 / 128 / 192 / 256 channels");
+  static_assert((C / 32) % kOutGroups == 0, "every output warp drains the same number of 32-column chunks");
 };
 
 struct MlpParams {
@@ -338,8 +339,8 @@ int launch_mlp(const void* A, int lda, const void* W1, int ldw1, const void* W2,
 int mlp_fused_bf16(const void* A, int lda, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
                    const float* b2, const float* gamma, const void* residual, int ldr, void* out, int ldc, int M, int C,
                    int H, int act, cudaStream_t stream) {
-  if ((C != 128 && C != 256) || H % kHC != 0 || H < 2 * kHC || M < 1) {
-    set_last_error("mlp_fused: needs C in {128, 256} and hidden %% 128 == 0, >= 256 (got C=%d hidden=%d)", C, H);
+  if ((C != 96 && C != 128 && C != 192 && C != 256) || H % kHC != 0 || H < 2 * kHC || M < 1) {
+    set_last_error("mlp_fused: needs C in {96, 128, 192, 256} and hidden %% 128 == 0, >= 256 (got C=%d hidden=%d)", C, H);
     return kUnsupported;
   }
   MlpParams p{};
@@ -355,8 +356,12 @@ int mlp_fused_bf16(const void* A, int lda, const void* W1, int ldw1, const float
   p.out.gamma = gamma;
   p.out.act = kActNone;
   p.out.has_res = residual != nullptr;
-  return C == 128 ? launch_mlp<128>(A, lda, W1, ldw1, W2, ldw2, residual, ldr, out, ldc, p, stream)
-                  : launch_mlp<256>(A, lda, W1, ldw1, W2, ldw2, residual, ldr, out, ldc, p, stream);
+  switch (C) {
+    case 96: return launch_mlp<96>(A, lda, W1, ldw1, W2, ldw2, residual, ldr, out, ldc, p, stream);
+    case 128: return launch_mlp<128>(A, lda, W1, ldw1, W2, ldw2, residual, ldr, out, ldc, p, stream);
+    case 192: return launch_mlp<192>(A, lda, W1, ldw1, W2, ldw2, residual, ldr, out, ldc, p, stream);
+    default: return launch_mlp<256>(A, lda, W1, ldw1, W2, ldw2, residual, ldr, out, ldc, p, stream);
+  }
 }
 
 }  // namespace tfimm

@@ -736,7 +736,8 @@ def test_gemm_short_contraction_streaming_kernel(M, K, N, act):
 
 @pytest.mark.parametrize("M,C,mult", [(256, 128, 4), (1000, 128, 4), (37 * 256 + 13, 128, 4), (150 * 256, 128, 4),
                                       (512, 256, 4), (777, 256, 4), (90 * 256 + 5, 256, 4), (3000, 128, 2),
-                                      (2048, 256, 3)])
+                                      (2048, 256, 3), (256, 96, 4), (75 * 256 + 77, 96, 4), (1000, 192, 4),
+                                      (80 * 256 + 3, 192, 4), (1024, 192, 2)])
 @pytest.mark.parametrize("act,with_gamma", [("gelu", True), ("gelu", False), ("swish", False)])
 def test_mlp_fused_equals_two_gemms(M, C, mult, act, with_gamma):
     """fc1 -> act -> fc2 -> * gamma -> + residual in one kernel (csrc/mlp_sm100.cu): same rounding points as the
@@ -775,7 +776,8 @@ def test_mlp_fused_equals_two_gemms(M, C, mult, act, with_gamma):
 
 def test_mlp_fused_rejects_other_shapes():
     ops = _ops()
-    assert not ops.mlp_fused_supported(96, 384) and not ops.mlp_fused_supported(512, 2048)
+    assert not ops.mlp_fused_supported(64, 256) and not ops.mlp_fused_supported(512, 2048)
+    assert ops.mlp_fused_supported(96, 384) and ops.mlp_fused_supported(192, 768)
     assert ops.mlp_fused_supported(128, 512) and ops.mlp_fused_supported(256, 1024)
     a = torch.zeros(256, 512, device="cuda", dtype=torch.bfloat16)
     w1 = torch.zeros(2048, 512, device="cuda", dtype=torch.bfloat16)
