@@ -141,7 +141,8 @@ int tfimm_b200_attention_f32(const float* qkv, float* out, const float* bias, co
                              long B, int N, int H, int dh, float scale, float* probs, const int* row_map,
                              int nw_img, void* stream);
 
-/* Swin (shifted-)window attention, bf16, head_dim 32, N = window_size^2 <= 64 tokens per window:
+/* Swin (shifted-)window attention, bf16, head_dim 32, N = window_size^2 <= 144 tokens per window (mma.sync; instantiated for
+ * 64 and 144 padded rows -- the latter serves the 12 x 12 windows of the *_window12_384 models):
  * softmax(scale q k^T + bias[h] + mask) v per (window, head) with the cyclic shift and window
  * partition/reverse folded into row addressing (row_map as above).  labels (optional, int32[nw_img*N]):
  * region ids of the shifted-window mask; tokens with different ids get -100 added, exactly the

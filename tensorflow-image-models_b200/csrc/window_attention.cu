@@ -1,4 +1,6 @@
-// Swin (shifted-)window attention, bf16, tokens per window N <= 64, head_dim 32.
+// Swin (shifted-)window attention on mma.sync, bf16, head_dim 32: tokens per window N <= 64, or N <= 144 (the 12 x 12
+// windows of the *_window12_384 models) in a second instantiation.  7 x 7 windows run on tcgen05
+// (window_attention_sm100.cu); this kernel covers the rest.
 //
 // Reference: WindowAttention.call (tfimm/architectures/swin.py:159-198) wrapped by
 // SwinTransformerBlock.call's tf.roll -> window_partition -> ... -> window_reverse -> tf.roll
@@ -6,8 +8,8 @@
 // row-index table (row_map): each warp gathers the q/k/v rows of its (window, head) straight from the
 // token-ordered qkv projection and scatters the result rows back to the same tokens.
 //
-// One warp per (window, head): q/k/v (N x 32 bf16 each, zero-padded to 64 rows) staged in swizzled
-// shared memory with cp.async; S = q k^T on mma.sync m16n8k16 (4 query tiles x 7 key tiles), then
+// One warp per (window, head): q/k/v (N x 32 bf16 each, zero-padded to ROWS = 64 / 144 rows) staged in swizzled
+// shared memory with cp.async; S = q k^T on mma.sync m16n8k16 (ROWS / 16 query tiles x ROWS / 8 key tiles), then
 // + relative-position bias[h] (+ -100 between tokens of different shift regions), fp32 softmax in
 // registers, P (bf16) V on mma.sync, 4-byte stores of the 16 x 32 output tile.
 #include "common.cuh"
@@ -16,20 +18,22 @@ namespace tfimm {
 namespace {
 
 constexpr int kWDH = 32;      // head dim
-constexpr int kWRows = 64;    // padded tokens per window
 constexpr int kWWarps = 4;
-constexpr int kTileBytes = kWRows * kWDH * 2;  // 4 KB per q / k / v tile
 
 // 64-byte rows: 4 chunks of 16 B; XOR with (row >> 1) & 3 spreads 8 consecutive rows over all banks.
 __device__ __forceinline__ uint32_t wswz(int row, int chunk) {
   return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
+template <int ROWS>   // padded tokens per window: 64 or 144
 __global__ void __launch_bounds__(kWWarps * 32)
 window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                              const float* __restrict__ bias, const int* __restrict__ row_map,
                              const int* __restrict__ labels, long total_pairs, int nw_img, int N, int H,
                              float scale) {
+  constexpr int kWRows = ROWS;
+  constexpr int kTileBytes = ROWS * kWDH * 2;   // 4 / 9 KB per q / k / v tile
+  constexpr int NT = ROWS / 8;                  // key tiles of 8
   extern __shared__ __align__(128) uint8_t smem[];  // kWWarps * 3 * kTileBytes
   __shared__ int s_rows[kWWarps][kWRows];
   __shared__ int s_lab[kWWarps][kWRows];
@@ -64,37 +68,15 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat1
 
   const int g = lane >> 2, t = lane & 3;
   const float* bias_h = bias + (long)h * N * N;
-  // Relative-position bias of one 16-query tile in mma accumulator layout.  It only depends on (head, row,
-  // key), so the tile for m-tile mt+1 is fetched while m-tile mt is being processed (and the first one while
-  // the q/k/v rows are still in flight): the L2 latency of these scattered 4-byte loads never stalls the math.
-  auto load_bias_tile = [&](int mt, float (&bz)[8][4]) {
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = min(nt * 8 + 2 * t + (e & 1), N - 1);
-        const int row = min(mt * 16 + g + ((e >> 1) ? 8 : 0), N - 1);
-        bz[nt][e] = __ldg(bias_h + (long)row * N + key);
-      }
-    }
-  };
-  float bz_next[8][4];
-  load_bias_tile(0, bz_next);
   cp_async_wait<0>();
   __syncwarp();
 
   const int mtiles = (N + 15) >> 4;
-  const int ntiles = (N + 7) >> 3;   // key tiles with at least one valid key (<= 8)
+  const int ntiles = (N + 7) >> 3;   // key tiles with at least one valid key (<= NT)
   const float l2e = 1.4426950408889634f;
 
 #pragma unroll 1
   for (int mt = 0; mt < mtiles; ++mt) {
-    float bz[8][4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) bz[nt][e] = bz_next[nt][e];
-    if (mt + 1 < mtiles) load_bias_tile(mt + 1, bz_next);
     uint32_t qf[2][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
@@ -102,9 +84,9 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat1
       const int chunk = ks * 2 + (lane >> 4);
       ldmatrix_x4(sQ + wswz(row, chunk), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
     }
-    float s[8][4];
+    float s[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
       if (nt < ntiles) {
         const int row = nt * 8 + (lane & 7);
@@ -120,14 +102,14 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat1
     const int lab0 = s_lab[warp][r0], lab1 = s_lab[warp][r1];
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = nt * 8 + 2 * t + (e & 1);
         const int row = (e >> 1) ? r1 : r0;
         float val = -INFINITY;
         if (key < N && row < N) {
-          val = fmaf(s[nt][e], scale, bz[nt][e]);
+          val = fmaf(s[nt][e], scale, __ldg(bias_h + (long)row * N + key));   // L1 / L2-resident table
           if (labels != nullptr && s_lab[warp][key] != ((e >> 1) ? lab1 : lab0)) val += -100.0f;
         } else if (key < N) {
           val = 0.f;  // padded query rows: keep finite, result is discarded
@@ -143,7 +125,7 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat1
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
     }
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float pv = exp2f(s[nt][e] - mx[e >> 1]);
@@ -163,7 +145,7 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat1
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < NT / 2; ++kk) {
       if (2 * kk < ntiles) {
         uint32_t a[4];
         a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
@@ -201,20 +183,29 @@ int window_attention_bf16(const void* qkv, void* out, const float* bias, const i
                           cudaStream_t stream) {
   TFIMM_CHECK_ARG(B > 0 && nw_img > 0 && N > 0 && H > 0, "window_attention: bad shape");
   TFIMM_CHECK_ARG(bias != nullptr && row_map != nullptr, "window_attention: bias and row_map are required");
-  if (dh != kWDH || N > kWRows) {
-    set_last_error("window_attention: bf16 kernel supports head_dim 32 and <= 64 tokens per window (got dh=%d N=%d)", dh, N);
+  if (dh != kWDH || N > 144) {
+    set_last_error("window_attention: bf16 kernel supports head_dim 32 and <= 144 tokens per window (got dh=%d N=%d)", dh, N);
     return kUnsupported;
   }
   const long pairs = (long)B * nw_img * H;
   const unsigned grid = (unsigned)((pairs + kWWarps - 1) / kWWarps);
-  constexpr int smem = kWWarps * 3 * kTileBytes;
-  static unsigned long long attr_devs = 0;
-  if (first_use_on_device(attr_devs)) {
-    TFIMM_CUDA_OK(cudaFuncSetAttribute(window_attention_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (N <= 64) {
+    constexpr int smem = kWWarps * 3 * 64 * kWDH * 2;
+    static unsigned long long attr_devs = 0;
+    if (first_use_on_device(attr_devs))
+      TFIMM_CUDA_OK(cudaFuncSetAttribute(window_attention_bf16_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    window_attention_bf16_kernel<64><<<grid, kWWarps * 32, smem, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), bias, row_map, labels,
+        pairs, nw_img, N, H, scale);
+  } else {
+    constexpr int smem = kWWarps * 3 * 144 * kWDH * 2;   // 108 KB: two CTAs per SM
+    static unsigned long long attr_devs = 0;
+    if (first_use_on_device(attr_devs))
+      TFIMM_CUDA_OK(cudaFuncSetAttribute(window_attention_bf16_kernel<144>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    window_attention_bf16_kernel<144><<<grid, kWWarps * 32, smem, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), bias, row_map, labels,
+        pairs, nw_img, N, H, scale);
   }
-  window_attention_bf16_kernel<<<grid, kWWarps * 32, smem, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), bias, row_map, labels,
-      pairs, nw_img, N, H, scale);
   TFIMM_LAUNCH_OK("window_attention_bf16_kernel");
   return kOk;
 }

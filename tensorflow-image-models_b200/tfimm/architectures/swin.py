@@ -282,9 +282,10 @@ class SwinTransformer(Model):
         scale = dh ** -0.5
         if qkv.dtype == torch.bfloat16 and dh == 32 and n <= 52:
             return ops.window_attention_tc(qkv, blk["bias_pad"], row_map, bits, B, nw, n, heads, dh, scale)
-        if qkv.dtype == torch.bfloat16 and dh == 32 and n <= 64:
+        if qkv.dtype == torch.bfloat16 and dh == 32 and n <= 144:
+            # mma.sync kernel: 8 x 8 windows, and the 12 x 12 windows of the *_window12_384 models
             return ops.window_attention(qkv, blk["bias"], row_map, labels, B, nw, n, heads, dh, scale)
-        # generic path: fp32 SIMT kernel (precision="fp32", or windows larger than 64 tokens)
+        # generic path: fp32 SIMT kernel (precision="fp32", other head dims, windows larger than 144 tokens)
         out = ops.attention(ops.cast(qkv, torch.float32), B * nw, n, heads, dh, scale, bias=blk["bias"], mask=mask,
                             row_map=row_map, nw_img=nw)
         return ops.cast(out, qkv.dtype)

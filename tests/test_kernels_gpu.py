@@ -391,7 +391,8 @@ def test_global_avg_pool(dtype):
     assert (out - x.float().mean(dim=(1, 2))).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("h,w,ws,shift,H", [(14, 14, 7, 3, 4), (14, 14, 7, 0, 4), (28, 21, 7, 3, 2), (8, 8, 4, 2, 3), (7, 7, 7, 0, 8)])
+@pytest.mark.parametrize("h,w,ws,shift,H", [(14, 14, 7, 3, 4), (14, 14, 7, 0, 4), (28, 21, 7, 3, 2), (8, 8, 4, 2, 3), (7, 7, 7, 0, 8),
+                                            (24, 24, 12, 6, 4), (24, 12, 12, 0, 2), (16, 16, 8, 4, 3), (20, 10, 10, 5, 2)])
 def test_window_attention_bf16(h, w, ws, shift, H):
     """Index-folded shifted-window attention vs explicit roll / partition / mask in torch."""
     from tfimm.architectures.swin import window_tables

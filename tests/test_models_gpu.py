@@ -175,6 +175,26 @@ def test_swin_bf16_parity(name):
     assert rel < BF16_TOL
 
 
+def test_swin_window12_bf16_runs_on_the_tensor_core_window_kernel():
+    """*_window12_384 registrations (144 tokens per window): the bf16 mma.sync window kernel, not the fp32 fallback."""
+    import tfimm
+    from tfimm.backend import ops
+
+    name = "swin_base_patch4_window12_384"
+    overrides = {"nb_blocks": (2, 2, 2, 2)}
+    _, _, _, out, ref = _run(name, "swin", "bf16", 1, overrides)
+    rel, ab = _nerr(out, ref)
+    print(f"{name} (2 blocks per stage) bf16: normalised {rel:.3e} abs {ab:.3e}")
+    assert rel < BF16_TOL
+    model = tfimm.create_model(name, precision="bf16", device="cuda", **overrides)
+    ops.trace = []
+    model(torch.zeros(1, 384, 384, 3, device="cuda"))
+    torch.cuda.synchronize()
+    fams = {t[0] for t in ops.trace}
+    ops.trace = None
+    assert "window_attention_bf16" in fams and "attention_f32" not in fams, fams
+
+
 def test_swin_return_features():
     import tfimm
     from oracle import params
