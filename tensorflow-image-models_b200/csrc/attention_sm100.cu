@@ -102,12 +102,16 @@ __device__ __forceinline__ float softmax_tile_unrolled(uint32_t t_row, int N, fl
 // persistent, warp-specialised, two-stage pipeline (one CTA per SM)
 // ---------------------------------------------------------------------------------------------------
 //   warp 0      TMA producer: Q (256 rows), K, V of work item i+1 while item i is being processed
-//   warp 1      tcgen05.mma issuer: S = Q K^T for both 128-query tiles, later O = P V for both
-//   warps 2..5  softmax / epilogue group A (queries 0..127,   TMEM columns   0..255)
-//   warps 6..9  softmax / epilogue group B (queries 128..255, TMEM columns 256..511)
-// A work item is one (image, head).  Per 128-query tile the TMEM region holds S (fp32, cols [0,npad)), then P
-// (bf16 packed, cols [0,npad/2)) written over the consumed scores, then O (cols [128,192)).
-constexpr int kP2Threads = 320;
+//   warps 1, 10 tcgen05.mma issuers, one per group: S = Q K^T of the group's query tile, later O = P V
+//   warps 2..5  softmax / epilogue group A (TMEM columns   0..255)
+//   warps 6..9  softmax / epilogue group B (TMEM columns 256..511)
+// A work item is one (image, head).  With two query tiles per item (197 tokens: 128 + 69 rows) the groups ALTERNATE
+// between the long and the short tile from item to item (group g takes tile (item index + g) & 1) and are driven by
+// separate MMA warps, so the group that had the short tile moves on to the next item (already in the other stage) while
+// the other one is still busy: an item costs (long + short) / 2 per group instead of `long` (with one MMA warp and a
+// fixed assignment group B idled ~40 % of every item).  Per tile the TMEM region holds S (fp32, cols [0,npad)), then
+// P (bf16 packed, cols [0,npad/2)) written over the consumed scores, then O (cols [128,192)).
+constexpr int kP2Threads = 352;
 constexpr int kP2QBytes = 256 * 128;
 constexpr int kP2StageBytes = kP2QBytes + 2 * kKVBytesMax;  // 96 KB
 constexpr int kP2SmemBytes = 2 * kP2StageBytes + 256 + 1024;
@@ -171,52 +175,49 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tma_load_3d(sV, &tmap_kv, full_bar(s), 2 * D + h * kDH, 0, b);
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------- MMA issuer --------------------------------------
-    const uint32_t idesc_s = umma_idesc_bf16_f32(kQRows, npad);
-    const uint32_t idesc_o = umma_idesc_bf16_f32(kQRows, kDH, /*b_mn_major=*/true);
-    const int ksteps = npad >> 4;
-    int it = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-      const int s = it & 1;
-      const uint32_t ph = (uint32_t)(it >> 1) & 1u, par = (uint32_t)it & 1u;
-      const uint32_t sQ = smem_base + s * kP2StageBytes, sK = sQ + kP2QBytes, sV = sK + kKVBytesMax;
-      mbar_wait(full_bar(s), ph);
-      for (int r = 0; r < mtiles; ++r) {
-        mbar_wait(tempty_bar(r), par ^ 1u);
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------ MMA issuer of group g (one warp each) ------------------------------
+    const int g = warp == 1 ? 0 : 1;
+    if (g < mtiles) {
+      const uint32_t idesc_s = umma_idesc_bf16_f32(kQRows, npad);
+      const uint32_t idesc_o = umma_idesc_bf16_f32(kQRows, kDH, /*b_mn_major=*/true);
+      const int ksteps = npad >> 4;
+      const uint32_t t0 = tmem_base + (uint32_t)(g * 256);
+      int it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)(it >> 1) & 1u, par = (uint32_t)it & 1u;
+        const int r = mtiles == 2 ? ((it + g) & 1) : 0;   // query tile of this group for this item
+        const uint32_t sQ = smem_base + s * kP2StageBytes, sK = sQ + kP2QBytes, sV = sK + kKVBytesMax;
+        mbar_wait(full_bar(s), ph);
+        mbar_wait(tempty_bar(g), par ^ 1u);
         tcgen05_fence_after();
         if (lane == 0) {
           const uint64_t dq = umma_desc_k_sw128(sQ + (uint32_t)r * (kQRows * 128)), dk = umma_desc_k_sw128(sK);
 #pragma unroll
           for (int k = 0; k < kDH / 16; ++k)
-            umma_bf16_ss(tmem_base + (uint32_t)(r * 256), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s,
-                         (uint32_t)(k != 0));
-          umma_commit(sfull_bar(r));
+            umma_bf16_ss(t0, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+          umma_commit(sfull_bar(g));
         }
         __syncwarp();
-      }
-      for (int r = 0; r < mtiles; ++r) {
-        mbar_wait(pready_bar(r), par);
+        mbar_wait(pready_bar(g), par);
         tcgen05_fence_after();
         if (lane == 0) {
-          const uint32_t t0 = tmem_base + (uint32_t)(r * 256);
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t dv = umma_desc_mn_sw128(sV + (uint32_t)(j * 2048), (uint32_t)(npad * 128));
             umma_bf16_ts(t0 + kOCol, t0 + (uint32_t)(j * 8), dv, idesc_o, (uint32_t)(j != 0));
           }
-          umma_commit(ofull_bar(r));
+          umma_commit(ofull_bar(g));
         }
         __syncwarp();
       }
     }
   } else {
     // ------------------------------- softmax + epilogue groups -------------------------------
-    const int r = (warp - 2) >> 2;  // 0: queries 0..127, 1: queries 128..255
+    const int g = (warp - 2) >> 2;  // group: TMEM region g, barriers g
     const int q = warp & 3;         // TMEM lane quarter
-    if (r < mtiles) {
-      const int row0 = r * kQRows + q * 32;  // first query row of this warp inside the image
-      const bool warp_has_rows = row0 < N;
-      const uint32_t t_row = tmem_base + (uint32_t)(r * 256) + ((uint32_t)(q * 32) << 16);
+    if (g < mtiles) {
+      const uint32_t t_row = tmem_base + (uint32_t)(g * 256) + ((uint32_t)(q * 32) << 16);
       const int nfull = npad >> 5;
       const bool tail16 = (npad & 16) != 0;
       const int nchunks = nfull + (tail16 ? 1 : 0);
@@ -238,7 +239,10 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const int s = it & 1;
         const uint32_t par = (uint32_t)it & 1u;
         const int b = item / H, h = item % H;
-        mbar_wait(sfull_bar(r), par);
+        const int r = mtiles == 2 ? ((it + g) & 1) : 0;   // this item's query tile for this group (alternates)
+        const int row0 = r * kQRows + q * 32;             // first query row of this warp inside the image
+        const bool warp_has_rows = row0 < N;
+        mbar_wait(sfull_bar(g), par);
         tcgen05_fence_after();
         float row_sum = 1.f;
         if (warp_has_rows && npad == 208) {
@@ -306,9 +310,9 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(pready_bar(r));
+        if (lane == 0) mbar_arrive(pready_bar(g));
 
-        mbar_wait(ofull_bar(r), par);
+        mbar_wait(ofull_bar(g), par);
         tcgen05_fence_after();
         uint32_t o0[32], o1[32];
         if (warp_has_rows) {
@@ -318,7 +322,7 @@ vit_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(r));  // the MMA warp may start the next item's S in this region
+        if (lane == 0) mbar_arrive(tempty_bar(g));  // the group's MMA warp may start the next item's S in this region
         if (warp_has_rows) {
           const float inv = 1.0f / row_sum;
           const uint32_t slab = smem_base + s * kP2StageBytes + (uint32_t)row0 * 128u;  // this warp's dead Q rows
