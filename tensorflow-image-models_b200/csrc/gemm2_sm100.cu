@@ -36,9 +36,12 @@ constexpr int kStageBytes = kABytes + kBBytes;  // per CTA
 constexpr uint32_t kTmemCols = kAccStages * kBlockN;  // 512: all of this SM's tensor memory
 constexpr int kCH = 32;        // output columns per epilogue chunk (both output types)
 
-template <typename OutT>
+// kWideEpi (fp32 output only): sixteen epilogue warps instead of eight.  With a short contraction (K <= 1024: the proj
+// GEMMs, 128 x 256 fp32 outputs + as many residual values per CTA every ~3 us) the eight-warp epilogue is the limiter
+// (ViT-B proj 79.5 -> 69.6 us); at K = 3072 the MMA time hides it either way and the extra warps cost ~1 %.
+template <typename OutT, bool kWideEpi = false>
 struct PairCfg {
-  static constexpr int kEpiGroups = sizeof(OutT) == 2 ? 4 : 2;  // epilogue warps per TMEM lane quarter
+  static constexpr int kEpiGroups = (sizeof(OutT) == 2 || kWideEpi) ? 4 : 2;  // epilogue warps per TMEM lane quarter
   static constexpr int kNumEpiWarps = 4 * kEpiGroups;
   static constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
   static constexpr int kSlabBytes = 32 * kCH * (int)sizeof(OutT);                     // 2 KB (bf16) / 4 KB (fp32)
@@ -49,13 +52,13 @@ struct PairCfg {
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
-template <typename OutT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<OutT>::kNumThreads, 1)
+template <typename OutT, bool kWideEpi = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<OutT, kWideEpi>::kNumThreads, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                               const __grid_constant__ CUtensorMap tmap_b,
                               const __grid_constant__ CUtensorMap tmap_c,
                               const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
-  using Cfg = PairCfg<OutT>;
+  using Cfg = PairCfg<OutT, kWideEpi>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kNumEpiWarps = Cfg::kNumEpiWarps;
   constexpr int kEpiGroups = Cfg::kEpiGroups;
@@ -212,10 +215,10 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
-template <typename OutT>
+template <typename OutT, bool kWideEpi = false>
 int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const void* residual, int ldr, void* C, int ldc,
                      const GemmParams& p, cudaStream_t stream) {
-  using Cfg = PairCfg<OutT>;
+  using Cfg = PairCfg<OutT, kWideEpi>;
   const int M = p.M, N = p.N, K = p.K;
   constexpr int out_dtype = sizeof(OutT) == 2 ? kBF16 : kF32;
   constexpr int row_bytes = kCH * (int)sizeof(OutT);  // 64 (bf16) or 128 (fp32): also the TMA swizzle span
@@ -229,7 +232,7 @@ int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const void*
   } else {
     tr = tc;
   }
-  auto kernel = gemm_bf16_tcgen05_pair_kernel<OutT>;
+  auto kernel = gemm_bf16_tcgen05_pair_kernel<OutT, kWideEpi>;
   static unsigned long long attr_devs = 0;  // per instantiation
   if (first_use_on_device(attr_devs)) {
     TFIMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -246,8 +249,9 @@ int launch_gemm_pair(const void* A, int lda, const void* W, int ldw, const void*
 
 int gemm_bf16_pair(const void* A, int lda, const void* W, int ldw, const void* residual, int ldr, void* C, int ldc,
                    const GemmParams& p, int out_dtype, cudaStream_t stream) {
-  return out_dtype == kBF16 ? launch_gemm_pair<__nv_bfloat16>(A, lda, W, ldw, residual, ldr, C, ldc, p, stream)
-                            : launch_gemm_pair<float>(A, lda, W, ldw, residual, ldr, C, ldc, p, stream);
+  if (out_dtype == kBF16) return launch_gemm_pair<__nv_bfloat16>(A, lda, W, ldw, residual, ldr, C, ldc, p, stream);
+  return p.K <= 1024 ? launch_gemm_pair<float, true>(A, lda, W, ldw, residual, ldr, C, ldc, p, stream)
+                     : launch_gemm_pair<float, false>(A, lda, W, ldw, residual, ldr, C, ldc, p, stream);
 }
 
 }  // namespace tfimm
