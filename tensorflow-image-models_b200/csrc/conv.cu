@@ -601,8 +601,11 @@ int se_gate(const float* pooled_sum, float inv_hw, const float* w_reduce, const 
   TFIMM_CHECK_ARG(B > 0 && C > 0 && rd > 0, "se_gate: bad shape");
   const size_t smem = (size_t)(C + rd) * sizeof(float);
   TFIMM_CHECK_ARG(smem <= 48 * 1024, "se_gate: C + rd too large (%d + %d)", C, rd);
-  se_gate_kernel<<<B, 256, smem, stream>>>(pooled_sum, inv_hw, w_reduce, b_reduce, w_expand, b_expand, gate, C, rd,
-                                           act, gate_act);
+  // both FCs are chains of L2 round trips whose length is C / blockDim (second FC) and rd / (4 warps) (first FC):
+  // 512 threads per image for wide layers (EfficientNet-B4: 1.08 -> 0.75 ms per step; 1024 threads: 0.80)
+  const int threads = C >= 512 ? 512 : 256;
+  se_gate_kernel<<<B, threads, smem, stream>>>(pooled_sum, inv_hw, w_reduce, b_reduce, w_expand, b_expand, gate, C, rd,
+                                               act, gate_act);
   TFIMM_LAUNCH_OK("se_gate_kernel");
   return kOk;
 }
