@@ -564,11 +564,7 @@ int im2col(const void* x, int in_dtype, void* out, int out_dtype, int B, int H, 
 #define TFIMM_I2C_STEM(IN, OUT, KS_T)                                                                         \
   im2col_kernel<IN, OUT, KS_T, 3><<<grid, 256, 0, stream>>>(reinterpret_cast<const IN*>(x), reinterpret_cast<OUT*>(out), \
                                                            B, H, W, C, groups, Ho, Wo, ks, stride, pad_t, pad_l, Kpad)
-  static const bool stem_tiled = [] {
-    const char* e = getenv("TFIMM_B200_STEM");  // "generic": per-element gather kernel (A/B)
-    return e == nullptr || e[0] != 'g';
-  }();
-  if (stem_tiled && C == 3 && groups == 1 && ks == 7 && stride == 2 && out_dtype == kBF16 && Kpad >= 147 &&
+  if (C == 3 && groups == 1 && ks == 7 && stride == 2 && out_dtype == kBF16 && Kpad >= 147 &&
       (in_dtype == kF32 || in_dtype == kBF16)) {
     const long ctas = (long)B * Ho * ((Wo + 31) / 32);
     if (in_dtype == kF32)
@@ -705,13 +701,8 @@ int dwconv_bias_act(const void* x, int dtype, const float* wgt, const float* bia
                   "dwconv: kernel size 3/5/7 and stride 1/2 are instantiated (got k=%d s=%d)", ks, stride);
   TFIMM_CHECK_ARG(dtype == kBF16 || dtype == kF32, "dwconv: dtype must be bf16 or f32");
   {
-    // bf16, k in {3,5}: TMA-halo shared-memory kernel (dwconv_act_tma_sm100.cu); TFIMM_B200_DWCONV_ACT=pairs
-    // selects the previous register-window kernel for A/B measurements
-    static const bool use_tma = [] {
-      const char* e = getenv("TFIMM_B200_DWCONV_ACT");
-      return e == nullptr || e[0] != 'p';
-    }();
-    if (use_tma) {
+    // bf16, k in {3,5}: TMA-halo shared-memory kernel (dwconv_act_tma_sm100.cu)
+    {
       const int st = dwconv_bias_act_tma(x, dtype, wgt, bias, out, pool_sum, B, H, W, C, ks, stride, pad_t, pad_l, Ho,
                                          Wo, act, stream);
       if (st != kUnsupported) return st;

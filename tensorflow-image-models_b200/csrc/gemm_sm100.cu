@@ -395,12 +395,6 @@ int pick_block_n(int M, int N) {
 // CTA-pair kernel (gemm2_sm100.cu) when its 256 x 256 tiles fill the machine at least as well as the best
 // one-CTA tiling: cost = waves x tile width, the pair kernel's MMA rate per SM being ~15% higher.
 bool prefer_pair(int M, int N) {
-  static const int mode = [] {
-    const char* e = getenv("TFIMM_B200_GEMM");  // "1cta" / "2cta" force one kernel (A/B measurements)
-    return e == nullptr ? 0 : (e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0));
-  }();
-  if (mode == 1) return false;
-  if (mode == 2) return true;
   if (N < 256 || M < 256) return false;
   const int sms = sm_count() > 0 ? sm_count() : 148;  // no device (host-side shape queries): B200
   const long tiles2 = (long)((M + 255) / 256) * ((N + 255) / 256);

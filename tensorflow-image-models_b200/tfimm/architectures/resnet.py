@@ -14,7 +14,6 @@ Not implemented (raise at construction): BlurPool anti-aliasing (1 registration)
 wider than 32 channels (resnext 32x8d and wider).
 """
 import math
-import os
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
@@ -296,7 +295,7 @@ class ResNet(Model):
         w, bias, gn = wb
         B = x.shape[0]
         if (k > 1 and gn is None and self.precision == "bf16" and isinstance(pad, int) and x.shape[-1] % 64 == 0
-                and w.shape[1] == k * k * x.shape[-1] and os.environ.get("TFIMM_B200_CONV", "implicit") == "implicit"):
+                and w.shape[1] == k * k * x.shape[-1]):
             # implicit GEMM: the A tiles are 4-D TMA boxes of the feature map, nothing is materialised
             return ops.conv_gemm(x, w, bias=bias, ks=k, stride=stride, pad=pad, act=act,
                                  residual=residual.contiguous() if residual is not None else None,
