@@ -240,3 +240,29 @@ def test_c_abi_library_exports_every_declared_symbol():
             want = ctypes.c_void_p if "*" in p else ctypes.c_float if p.startswith("float") else \
                 ctypes.c_long if p.startswith("long") else ctypes.c_int
             assert ct is want, (name, p, ct)
+
+
+def test_every_kernel_of_the_library_belongs_to_a_bench_family():
+    """bench.py's roofline table and tools/ncu_traffic.py group launches by kernel family: every __global__ function of
+    the built library must map to one (a new kernel without a family would silently drop out of `roofline.traffic`)."""
+    import re
+    import shutil
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    if shutil.which("cuobjdump") is None or shutil.which("c++filt") is None:
+        pytest.skip("cuobjdump / c++filt not available")
+    root = Path(__file__).resolve().parent.parent
+    lib = root / "tensorflow-image-models_b200" / "tfimm" / "backend" / "libtfimm_b200.so"
+    if not lib.exists():
+        pytest.skip("library not built")
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", str(lib)], capture_output=True, text=True).stdout
+    names = sorted(set(re.findall(r"Function (\S+?):", out)))
+    assert len(names) > 100, len(names)
+    dem = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
+    sys.path.insert(0, str(root / "tools"))
+    import ncu_traffic
+
+    unmapped = [d for d in dem if ncu_traffic.family_of(d).startswith("other:")]
+    assert not unmapped, unmapped[:5]
