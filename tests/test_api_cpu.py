@@ -266,3 +266,24 @@ def test_every_kernel_of_the_library_belongs_to_a_bench_family():
 
     unmapped = [d for d in dem if ncu_traffic.family_of(d).startswith("other:")]
     assert not unmapped, unmapped[:5]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU stand-in the driver times beside the GPU arm) runs without a GPU and prints
+    one JSON line with the contract's keys."""
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ref-batch", "2", "--model", "vit_tiny_patch16_224"], capture_output=True, text=True,
+                         timeout=600, cwd=str(root))
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "images/sec"
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0
